@@ -179,6 +179,9 @@ int chz_pdws(chz_t* h, const chz_pdw_params_t* params, chz_pdw_t* out, uint64_t 
 /* Same over a caller-owned device matrix y_dev[nrows][M] (natural channel order). */
 int chz_pdws_dev(chz_t* h, const chz_pdw_params_t* params, const chz_cf32* y_dev, uint64_t nrows,
                  chz_pdw_t* out, uint64_t cap, uint64_t* n);
+/* Records of the last chz_pdws* run (cached in the handle), without recomputing: use after a
+ * CHZ_ECAPACITY answer.  *n = record count. */
+int chz_pdws_fetch(const chz_t* h, chz_pdw_t* out, uint64_t cap, uint64_t* n);
 /* Per-channel noise floor (natural order, M doubles) of the last chz_pdws* call. */
 int chz_pdw_noise_floor(const chz_t* h, double* nf, uint32_t cap);
 

@@ -1,0 +1,280 @@
+"""Host-side mirror of the reference's interface for the hot path, on top of the C ABI.
+
+The reference's "API" for this path is a pair of MATLAB scripts plus the toolbox object they call:
+
+    convert_my_iq_to_mat.m:38-118   .iq -> variables iq, fs, fc, dur, bw, gain, bitWidth, sampleStartTime, ...
+    channelizer = dsp.Channelizer(M); y = channelizer(iq); centerFrequencies(channelizer, fs)
+                                     (create_pdws_channelized.m:33,42,57; channelizer_example.m:31,56,60)
+    create_pdws_channelized.m        pdw.toa / pdw.freq / pdw.pw / pdw.snr / pdw.sat
+
+so this module offers read_iq(), Channelizer (same construct / call / centerFrequencies / reset
+verbs, same property names) and create_pdws_channelized().  All arithmetic runs in the CUDA library;
+numpy is only the container for host buffers.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import ChannelizerError, IqInfo, Pdw, PdwParams, check, lib
+
+
+# ------------------------------------------------------------------------------------------------
+# R1  .iq reader / writer
+# ------------------------------------------------------------------------------------------------
+class IqRecording:
+    """Variables convert_my_iq_to_mat.m:118 saves, under the same names."""
+
+    def __init__(self, info: IqInfo, iq: np.ndarray):
+        self.iq = iq                                  # [N, 2] int8|int16 (MATLAB holds it as [2, N])
+        self.fs = float(info.fs_sps)
+        self.fc = float(info.fc_hz)
+        self.bw = float(info.bw_hz)
+        self.gain = float(info.gain_db)
+        self.bitWidth = int(info.bit_width)
+        self.sampleStartTime = float(info.sample_start_time)
+        self.linkSpeed = int(info.link_speed)
+        self.boardName = info.board_name.decode(errors="replace")
+        self.serialNo = info.serial_number.decode(errors="replace")
+        self.fpgaVersion = info.fpga_version.decode(errors="replace")
+        self.fwVersion = info.fw_version.decode(errors="replace")
+        self.fileFormat = int(info.format)
+        self.numSamples = int(info.num_samples)
+        self.dur = self.numSamples / self.fs if self.fs else 0.0   # convert_my_iq_to_mat.m:106
+        self.info = info
+
+
+def read_iq(path) -> IqRecording:
+    """Parse a recording exactly as convert_my_iq_to_mat.m:38-102 does.  Errors mirror the script's:
+    unknown magic -> 'Unsupported endianness', bad bitWidth -> 'Unsupported bit width', payload
+    length != numSamples -> the assert at :102."""
+    L = lib()
+    handle = C.c_void_p()
+    info = IqInfo()
+    check(L.chz_open_iq(os.fsencode(path), C.byref(handle), C.byref(info)), f"chz_open_iq({path})")
+    try:
+        dt = np.int8 if info.bit_width <= 8 else np.dtype("<i2")
+        n = int(info.num_samples)
+        ptr = L.chz_iq_payload(handle)
+        if n:
+            buf = (C.c_char * (n * info.bytes_per_sample)).from_address(ptr)
+            iq = np.frombuffer(buf, dtype=dt).reshape(n, 2).copy()
+        else:
+            iq = np.empty((0, 2), dtype=dt)
+    finally:
+        L.chz_close_iq(handle)
+    return IqRecording(info, iq)
+
+
+def write_iq(path, iq, *, fs, fc=0, bw=0, gain=0.0, bitWidth=16, sampleStartTime=0.0, fileFormat=3,
+             linkSpeed=0, boardName="", serialNo="", fpgaVersion="", fwVersion=""):
+    """Write a recording the way the recorders do (header struct, then raw interleaved payload;
+    cpp/blade_record_iq_12bit.cpp:320-323).  iq: [N, 2] int8 (bitWidth <= 8) or int16."""
+    dt = np.int8 if bitWidth <= 8 else np.dtype("<i2")
+    iq = np.ascontiguousarray(iq, dtype=dt).reshape(-1, 2)
+    info = IqInfo()
+    info.format = fileFormat
+    info.link_speed = linkSpeed
+    info.fc_hz = int(fc)
+    info.bw_hz = int(bw)
+    info.fs_sps = int(fs)
+    info.gain_db = float(gain)
+    info.num_samples = iq.shape[0]
+    info.bit_width = bitWidth
+    info.board_name = boardName.encode()[:16]
+    info.serial_number = serialNo.encode()[:16]
+    info.fpga_version = fpgaVersion.encode()[:16]
+    info.fw_version = fwVersion.encode()[:16]
+    info.sample_start_time = float(sampleStartTime)
+    check(lib().chz_write_iq(os.fsencode(path), C.byref(info), iq.ctypes.data_as(C.c_void_p)), "chz_write_iq")
+
+
+def design_prototype(M, NumTapsPerBand=12, StopbandAttenuation=80.0) -> np.ndarray:
+    taps = np.empty(M * NumTapsPerBand, dtype=np.float32)
+    check(lib().chz_design_prototype(M, NumTapsPerBand, float(StopbandAttenuation), taps.ctypes.data_as(C.c_void_p)),
+          "chz_design_prototype")
+    return taps
+
+
+# ------------------------------------------------------------------------------------------------
+# R4-R7  dsp.Channelizer mirror
+# ------------------------------------------------------------------------------------------------
+class Channelizer:
+    """channelizer = dsp.Channelizer(M)   (create_pdws_channelized.m:33)
+
+    NumFrequencyBands / NumTapsPerBand / StopbandAttenuation / OversamplingRatio follow the toolbox
+    property names and defaults (12 taps per band, 80 dB, critically sampled).  `taps` overrides the
+    designed prototype (length must be a multiple of M).  Stateful like the System object: FIR
+    history carries across calls (channelizer_example.m:50-56) until reset().
+    """
+
+    def __init__(self, NumFrequencyBands=8, NumTapsPerBand=12, StopbandAttenuation=80.0, OversamplingRatio=1,
+                 taps=None):
+        self.NumFrequencyBands = int(NumFrequencyBands)
+        self.OversamplingRatio = int(OversamplingRatio)
+        if taps is None:
+            taps = design_prototype(self.NumFrequencyBands, NumTapsPerBand, StopbandAttenuation)
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        self.NumTapsPerBand = len(taps) // self.NumFrequencyBands
+        self.StopbandAttenuation = float(StopbandAttenuation)
+        self._h = C.c_void_p()
+        check(lib().chz_create(self.NumFrequencyBands, taps.ctypes.data_as(C.c_void_p), len(taps),
+                               self.OversamplingRatio, C.byref(self._h)), "chz_create")
+        self._taps = taps
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().chz_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        check(lib().chz_reset(self._h), "chz_reset")
+
+    def release(self):      # System-object verb
+        self.reset()
+
+    # -- properties --------------------------------------------------------------------------
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def DecimationFactor(self):
+        return lib().chz_decimation(self._h)
+
+    def coeffs(self):
+        """Prototype low-pass coefficients (toolbox: coeffs(channelizer))."""
+        return self._taps.copy()
+
+    def centerFrequencies(self, fs):
+        """centerFrequencies(channelizer, fs) as the reference uses it: against the fftshift-ed columns
+        (create_pdws_channelized.m:42,60,80) -> ascending (-M/2 .. M/2-1) * fs / M."""
+        M = self.NumFrequencyBands
+        nat = np.array([lib().chz_channel_freq(self._h, k, float(fs)) for k in range(M)])
+        return np.fft.fftshift(nat)
+
+    def set_stream(self, cuda_stream_ptr):
+        check(lib().chz_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "chz_set_stream")
+
+    def set_option(self, opt, value):
+        check(lib().chz_set_option(self._h, opt, int(value)), "chz_set_option")
+
+    @property
+    def kernel_launches(self):
+        return int(lib().chz_kernel_launches(self._h))
+
+    # -- processing --------------------------------------------------------------------------
+    def rows_for(self, nsamp):
+        return int(lib().chz_rows_for(self._h, int(nsamp)))
+
+    def __call__(self, iq, bitWidth, out=None):
+        """y = channelizer(iq): iq is the RAW recording payload ([N, 2] int8/int16, as read_iq
+        returns it); normalisation by 2^(bitWidth-1) (create_pdws_channelized.m:35-38) happens on the
+        GPU.  Returns complex64 [rows, M], natural FFT channel order (apply np.fft.fftshift(y, axes=1)
+        for the reference's :60)."""
+        want = np.int8 if bitWidth <= 8 else np.dtype("<i2")
+        iq = np.ascontiguousarray(iq)
+        if iq.dtype != want:
+            raise TypeError(f"bitWidth {bitWidth} needs {want} samples, got {iq.dtype}")
+        nsamp = iq.size // 2
+        M = self.NumFrequencyBands
+        rows = self.rows_for(nsamp)
+        if out is None:
+            out = np.empty((rows, M), dtype=np.complex64)
+        n = C.c_uint64(0)
+        check(lib().chz_process(self._h, iq.ctypes.data_as(C.c_void_p), nsamp, bitWidth,
+                                out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(n)), "chz_process")
+        return out[: n.value]
+
+    def process_ptr(self, iq_ptr, nsamp, bitWidth, out_ptr, out_cap_rows, device=True):
+        """Raw-pointer entry (device pointers by default): returns rows produced.  Asynchronous on the
+        handle's stream for device pointers."""
+        n = C.c_uint64(0)
+        fn = lib().chz_process_dev if device else lib().chz_process
+        check(fn(self._h, C.c_void_p(iq_ptr), int(nsamp), int(bitWidth), C.c_void_p(out_ptr), int(out_cap_rows),
+                 C.byref(n)), "chz_process_dev" if device else "chz_process")
+        return int(n.value)
+
+    def synchronize(self):
+        check(lib().chz_synchronize(self._h), "chz_synchronize")
+
+    def fft_rows_ptr(self, u_ptr, y_ptr, nrows):
+        check(lib().chz_fft_rows_dev(self._h, C.c_void_p(u_ptr), C.c_void_p(y_ptr), int(nrows)), "chz_fft_rows_dev")
+
+    # -- PDWs ----------------------------------------------------------------------------------
+    def _pdw_call(self, fn, params, *lead):
+        n = C.c_uint64(0)
+        rc = fn(self._h, C.byref(params), *lead, None, 0, C.byref(n))
+        if rc not in (_lib.CHZ_OK, _lib.CHZ_ECAPACITY):
+            check(rc, "chz_pdws")
+        cnt = int(n.value)
+        arr = (Pdw * max(cnt, 1))()
+        if cnt:   # the run above cached its records in the handle; copy them out without recomputing
+            check(lib().chz_pdws_fetch(self._h, C.cast(arr, C.c_void_p), cnt, C.byref(n)), "chz_pdws_fetch")
+        nf = np.empty(self.NumFrequencyBands, dtype=np.float64)
+        check(lib().chz_pdw_noise_floor(self._h, nf.ctypes.data_as(C.c_void_p), len(nf)), "chz_pdw_noise_floor")
+        return [arr[i] for i in range(cnt)], nf
+
+    def pdws(self, fs, fc=0.0, sampleStartTime=0.0, SNR_THRESHOLD=15.0, sat_level=0.9999,
+             reproduce_phase_bug=False):
+        """PDWs over everything processed since reset (create_pdws_channelized.m:60-136).
+        -> (list of Pdw records in the reference's order, noise floor per natural channel)."""
+        prm = PdwParams(float(SNR_THRESHOLD), float(sat_level), float(fc), float(fs), float(sampleStartTime),
+                        int(bool(reproduce_phase_bug)), 0)
+        return self._pdw_call(lib().chz_pdws, prm)
+
+    def pdws_ptr(self, y_ptr, nrows, fs, fc=0.0, sampleStartTime=0.0, SNR_THRESHOLD=15.0, sat_level=0.9999,
+                 reproduce_phase_bug=False):
+        prm = PdwParams(float(SNR_THRESHOLD), float(sat_level), float(fc), float(fs), float(sampleStartTime),
+                        int(bool(reproduce_phase_bug)), 0)
+        return self._pdw_call(lib().chz_pdws_dev, prm, C.c_void_p(y_ptr), int(nrows))
+
+
+def unpack_ptr(iq_ptr, nsamp, bitWidth, out_ptr, stream_ptr=0):
+    """K1 alone on device pointers (create_pdws_channelized.m:35-38)."""
+    check(lib().chz_unpack_dev(C.c_void_p(iq_ptr), int(nsamp), int(bitWidth), C.c_void_p(out_ptr),
+                               C.c_void_p(stream_ptr or 0)), "chz_unpack_dev")
+
+
+# ------------------------------------------------------------------------------------------------
+# create_pdws_channelized.m as a function
+# ------------------------------------------------------------------------------------------------
+def create_pdws_channelized(recordings, M=None, NumTapsPerBand=12, SNR_THRESHOLD=15.0,
+                            reproduce_phase_bug=False, taps=None):
+    """The reference script as a function: for each recording (path or IqRecording) build a fresh
+    channelizer with M = fs*1e-6 bands unless given (:31-33), channelize, extract PDWs and
+    concatenate (:16-20,124-128).  M must be a power of two in [8, 4096] in this build.
+    Returns dict(toa, freq, pw, snr, sat, amp, channel) of numpy arrays."""
+    out = {k: [] for k in ("toa", "freq", "pw", "snr", "sat", "amp", "channel")}
+    for rec in recordings:
+        if not isinstance(rec, IqRecording):
+            rec = read_iq(rec)
+        m = int(M) if M else int(round(rec.fs * 1e-6))            # :31
+        ch = Channelizer(m, NumTapsPerBand=NumTapsPerBand, taps=taps)   # :33
+        try:
+            ch.set_option(_lib.CHZ_OPT_RETAIN, 1)
+            n = C.c_uint64(0)
+            iq = np.ascontiguousarray(rec.iq)
+            check(lib().chz_process(ch.handle, iq.ctypes.data_as(C.c_void_p), iq.shape[0], rec.bitWidth,
+                                    None, 0, C.byref(n)), "chz_process")                     # :35-57
+            recs, _ = ch.pdws(rec.fs, rec.fc, rec.sampleStartTime, SNR_THRESHOLD,
+                              reproduce_phase_bug=reproduce_phase_bug)                       # :60-136
+        finally:
+            ch.close()
+        for r in recs:
+            out["toa"].append(r.toa_s); out["freq"].append(r.freq_hz); out["pw"].append(r.pw_s)
+            out["snr"].append(r.snr_db); out["sat"].append(bool(r.saturated)); out["amp"].append(r.amp)
+            out["channel"].append(r.channel)
+    return {k: np.asarray(v) for k, v in out.items()}
+
+
+__all__ = ["IqRecording", "read_iq", "write_iq", "design_prototype", "Channelizer", "unpack_ptr",
+           "create_pdws_channelized", "ChannelizerError"]

@@ -1,0 +1,585 @@
+// libchannelizer: C ABI implementation (handles, streaming state, launches, host pipeline).
+// See include/channelizer.h for the contract and the reference lines each entry point replaces.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "chz_internal.h"
+#include "chz_kernels.cuh"
+
+namespace chzi {
+
+static thread_local std::string g_cuda_err;
+
+void set_cuda_error(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s: %s (%s) at %s:%d", what, cudaGetErrorString(e), cudaGetErrorName(e), file, line);
+  g_cuda_err = buf;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch tables
+// ------------------------------------------------------------------------------------------------
+struct LaunchPlan { dim3 grid; int span_rows; long long spans_per_phase; };
+
+static LaunchPlan plan_spans(const ::chz* h, long long nrows, int P, int groups_per_block, int blocks_per_sm,
+                             int max_blocks_override = 0) {
+  LaunchPlan lp;
+  const long long rows_per_phase = (nrows + h->os - 1) / h->os;
+  const long long max_blocks = max_blocks_override ? max_blocks_override : (long long)h->sm_count * blocks_per_sm;
+  const long long total_groups = max_blocks * groups_per_block;
+  long long sr = (rows_per_phase + total_groups * 4 - 1) / (total_groups * 4);
+  sr = (sr + P - 1) / P * P;
+  const long long lo = 4LL * P, hi = (4096LL / P) * P;
+  if (sr < lo) sr = lo;
+  if (sr > hi) sr = hi;
+  lp.span_rows = (int)sr;
+  lp.spans_per_phase = (rows_per_phase + sr - 1) / sr;
+  const long long nspans = lp.spans_per_phase * h->os;
+  long long blocks = (nspans + groups_per_block - 1) / groups_per_block;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  lp.grid = dim3((unsigned)blocks);
+  return lp;
+}
+
+template <int M, int P, bool IN16>
+static int launch_fused(::chz* h, ChanParams prm, cudaStream_t st) {
+  typedef FusedCfg<M, P> CF;
+  auto kern = k_chan_fused<M, P, IN16>;
+  static thread_local int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+    int nb = 0;
+    CHZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, CF::NT, CF::SMEM));
+    blocks_per_sm = nb > 0 ? nb : 1;
+  }
+  const LaunchPlan lp = plan_spans(h, prm.nrows, P, CF::G, blocks_per_sm);
+  prm.span_rows = lp.span_rows;
+  prm.spans_per_phase = lp.spans_per_phase;
+  kern<<<lp.grid, CF::NT, CF::SMEM, st>>>(prm);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  return CHZ_OK;
+}
+
+template <int P, bool IN16>
+static int launch_fir(::chz* h, ChanParams prm, float2* u, cudaStream_t st) {
+  const int bpb = prm.M < 128 ? prm.M : 128, nbb = prm.M / bpb, groups = 128 / bpb;
+  // blocks per SM by registers: 128 threads, <= ~96 regs -> 5; keep 4 resident per SM and branch block
+  LaunchPlan lp = plan_spans(h, prm.nrows, P, groups, 4, (h->sm_count * 4 / nbb) > 0 ? (h->sm_count * 4 / nbb) : 1);
+  prm.span_rows = lp.span_rows;
+  prm.spans_per_phase = lp.spans_per_phase;
+  const unsigned grid = lp.grid.x * (unsigned)nbb;
+  k_fir<P, IN16><<<grid, 128, 0, st>>>(prm, u);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  return CHZ_OK;
+}
+
+template <int M, int ROWS, int NT>
+static int launch_fft_rows_t(::chz* h, const float2* u, float2* y, long long nrows, cudaStream_t st) {
+  auto kern = k_fft_rows<M, ROWS, NT>;
+  const size_t smem = (size_t)(2 * ROWS * RowStride<M>::value + M) * sizeof(float2);
+  static thread_local int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CHZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, smem));
+    blocks_per_sm = nb > 0 ? nb : 1;
+  }
+  long long blocks = (nrows + ROWS - 1) / ROWS;
+  const long long maxb = (long long)h->sm_count * blocks_per_sm;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) return CHZ_OK;
+  kern<<<(unsigned)blocks, NT, smem, st>>>(u, y, h->d_tw, nrows);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  return CHZ_OK;
+}
+
+static int launch_fft_rows(::chz* h, const float2* u, float2* y, long long nrows, cudaStream_t st) {
+  switch (h->M) {
+    case 8: return launch_fft_rows_t<8, 256, 256>(h, u, y, nrows, st);
+    case 16: return launch_fft_rows_t<16, 128, 256>(h, u, y, nrows, st);
+    case 32: return launch_fft_rows_t<32, 64, 256>(h, u, y, nrows, st);
+    case 64: return launch_fft_rows_t<64, 32, 256>(h, u, y, nrows, st);
+    case 128: return launch_fft_rows_t<128, 16, 256>(h, u, y, nrows, st);
+    case 256: return launch_fft_rows_t<256, 16, 256>(h, u, y, nrows, st);
+    case 512: return launch_fft_rows_t<512, 8, 256>(h, u, y, nrows, st);
+    case 1024: return launch_fft_rows_t<1024, 4, 256>(h, u, y, nrows, st);
+    case 2048: return launch_fft_rows_t<2048, 2, 256>(h, u, y, nrows, st);
+    case 4096: return launch_fft_rows_t<4096, 1, 256>(h, u, y, nrows, st);
+    default: return CHZ_EINVAL;
+  }
+}
+
+template <bool IN16>
+static int launch_fir_dispatch(::chz* h, const ChanParams& prm, float2* u, cudaStream_t st) {
+  switch (h->P) {
+    case 4: return launch_fir<4, IN16>(h, prm, u, st);
+    case 8: return launch_fir<8, IN16>(h, prm, u, st);
+    case 12: return launch_fir<12, IN16>(h, prm, u, st);
+    case 16: return launch_fir<16, IN16>(h, prm, u, st);
+    case 24: return launch_fir<24, IN16>(h, prm, u, st);
+    case 32: return launch_fir<32, IN16>(h, prm, u, st);
+    default: {
+      const long long total = prm.nrows * prm.M;
+      long long blocks = (total + 255) / 256;
+      const long long maxb = (long long)h->sm_count * 8;
+      if (blocks > maxb) blocks = maxb;
+      k_fir_any<IN16><<<(unsigned)blocks, 256, 0, st>>>(prm, (int)h->P, u);
+      h->launches++;
+      CHZ_CUDA(cudaGetLastError());
+      return CHZ_OK;
+    }
+  }
+}
+
+#define CHZ_FUSED_P(MV, IN16V)                                                   \
+  switch (h->P) {                                                                \
+    case 8: return launch_fused<MV, 8, IN16V>(h, prm, st);                       \
+    case 12: return launch_fused<MV, 12, IN16V>(h, prm, st);                     \
+    case 16: return launch_fused<MV, 16, IN16V>(h, prm, st);                     \
+    default: return 1;                                                           \
+  }
+
+// returns 1 when no fused instantiation exists for (M, P)
+template <bool IN16>
+static int launch_fused_dispatch(::chz* h, const ChanParams& prm, cudaStream_t st) {
+  switch (h->M) {
+    case 8: CHZ_FUSED_P(8, IN16)
+    case 16: CHZ_FUSED_P(16, IN16)
+    case 32: CHZ_FUSED_P(32, IN16)
+    case 64: CHZ_FUSED_P(64, IN16)
+    case 128: CHZ_FUSED_P(128, IN16)
+    case 256: CHZ_FUSED_P(256, IN16)
+    case 512: CHZ_FUSED_P(512, IN16)
+    default: return 1;
+  }
+}
+
+static bool fused_available(const ::chz* h) {
+  return h->M <= 512 && (h->P == 8 || h->P == 12 || h->P == 16);
+}
+
+static int ensure_taps(::chz* h, uint32_t bw) {
+  if (h->d_taps[bw]) return CHZ_OK;
+  std::vector<float> scaled(h->L);
+  const float s = std::ldexp(1.0f, -(int)(bw - 1));   // exact power of two (create_pdws_channelized.m:35-37)
+  for (uint32_t i = 0; i < h->L; i++) scaled[i] = h->taps[i] * s;
+  CHZ_CUDA(cudaMalloc(&h->d_taps[bw], sizeof(float) * h->L));
+  CHZ_CUDA(cudaMemcpy(h->d_taps[bw], scaled.data(), sizeof(float) * h->L, cudaMemcpyHostToDevice));
+  return CHZ_OK;
+}
+
+// One launch (or FIR + FFT pair) over `nsamp` new device-resident samples; updates the stream state.
+static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, float2* out_dev,
+                     uint64_t* nrows_out, cudaStream_t st) {
+  const bool in16 = bw > 8;
+  const size_t bps = in16 ? 4 : 2;
+  const uint64_t rows_new = (h->consumed + nsamp) / h->D - h->rows_done;
+  int rc = ensure_taps(h, bw);
+  if (rc) return rc;
+  if (rows_new > 0) {
+    ChanParams prm;
+    memset(&prm, 0, sizeof prm);
+    prm.in = iq_dev; prm.hist = h->d_hist[h->hist_cur];
+    prm.in_base = (long long)h->consumed; prm.n_in = (long long)nsamp; prm.hist_base = (long long)h->hist_base;
+    prm.taps = h->d_taps[bw]; prm.tw = h->d_tw; prm.out = out_dev;
+    prm.row_base = (long long)h->rows_done; prm.nrows = (long long)rows_new;
+    prm.M = (int)h->M; prm.D = (int)h->D; prm.os = (int)h->os;
+    bool fused = fused_available(h) && h->force_path != 2;
+    if (h->force_path == 1 && !fused) return CHZ_EINVAL;
+    if (fused) {
+      rc = in16 ? launch_fused_dispatch<true>(h, prm, st) : launch_fused_dispatch<false>(h, prm, st);
+      if (rc == 1) return CHZ_EINVAL;
+      if (rc) return rc;
+    } else {
+      // split path: FIR rows -> the output buffer itself (in place), then the row FFT over it
+      rc = in16 ? launch_fir_dispatch<true>(h, prm, out_dev, st) : launch_fir_dispatch<false>(h, prm, out_dev, st);
+      if (rc) return rc;
+      rc = launch_fft_rows(h, out_dev, out_dev, (long long)rows_new, st);
+      if (rc) return rc;
+    }
+  }
+  // history for the next call: everything from the oldest sample the next row can touch
+  const uint64_t end = h->consumed + nsamp;
+  const uint64_t next_newest = (h->rows_done + rows_new) * (uint64_t)h->D;
+  const uint64_t need_from = next_newest >= (uint64_t)(h->L - 1) ? next_newest - (h->L - 1) : 0;
+  const uint64_t from = need_from < end ? need_from : end;
+  char* dst = (char*)h->d_hist[1 - h->hist_cur];
+  uint64_t written = 0;
+  if (from < h->consumed) {   // part still inside the old history
+    const uint64_t a = from > h->hist_base ? from : h->hist_base;
+    const uint64_t n_old = h->consumed - a;
+    if (n_old)
+      CHZ_CUDA(cudaMemcpyAsync(dst, (const char*)h->d_hist[h->hist_cur] + (a - h->hist_base) * bps, n_old * bps,
+                               cudaMemcpyDeviceToDevice, st));
+    written = n_old;
+    h->hist_base = a;
+    if (nsamp) CHZ_CUDA(cudaMemcpyAsync(dst + written * bps, iq_dev, nsamp * bps, cudaMemcpyDeviceToDevice, st));
+    written += nsamp;
+  } else {
+    const uint64_t n_new = end - from;
+    if (n_new)
+      CHZ_CUDA(cudaMemcpyAsync(dst, (const char*)iq_dev + (from - h->consumed) * bps, n_new * bps,
+                               cudaMemcpyDeviceToDevice, st));
+    written = n_new;
+    h->hist_base = from;
+  }
+  h->hist_len = written;
+  h->hist_cur = 1 - h->hist_cur;
+  h->consumed = end;
+  h->rows_done += rows_new;
+  if (nrows_out) *nrows_out = rows_new;
+  return CHZ_OK;
+}
+
+static int ensure_store(::chz* h, uint64_t rows_needed) {
+  if (rows_needed <= h->store_cap) return CHZ_OK;
+  uint64_t cap = h->store_cap * 2;
+  if (cap < rows_needed) cap = rows_needed;
+  float2* nb = nullptr;
+  CHZ_CUDA(cudaMalloc(&nb, cap * h->M * sizeof(float2)));
+  if (h->store_rows) {
+    CHZ_CUDA(cudaMemcpyAsync(nb, h->d_store, h->store_rows * h->M * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
+    CHZ_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  if (h->d_store) CHZ_CUDA(cudaFree(h->d_store));
+  h->d_store = nb;
+  h->store_cap = cap;
+  return CHZ_OK;
+}
+
+static int check_stream_args(::chz* h, uint64_t nsamp, uint32_t bw) {
+  if (bw == 0 || bw > 16) return CHZ_EBITWIDTH;
+  if (h->consumed + nsamp > (1ULL << 62)) return CHZ_EINVAL;
+  if (h->bit_width && h->bit_width != bw) return CHZ_ESTATE;   // one sample format per stream; chz_reset to change
+  return CHZ_OK;
+}
+
+}  // namespace chzi
+
+using namespace chzi;
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* chz_strerror(int code) {
+  switch (code) {
+    case CHZ_OK: return "ok";
+    case CHZ_EINVAL: return "invalid argument";
+    case CHZ_EIO: return "I/O error";
+    case CHZ_EFORMAT: return "Unsupported endianness (unknown .iq magic)";
+    case CHZ_EBITWIDTH: return "Unsupported bit width";
+    case CHZ_ESIZE: return "payload length does not match numSamples";
+    case CHZ_ENOMEM: return "out of memory";
+    case CHZ_ECUDA: return "CUDA error";
+    case CHZ_ENODEVICE: return "no usable sm_100 GPU (libchannelizer has no CPU path)";
+    case CHZ_ECAPACITY: return "output buffer too small";
+    case CHZ_ESTATE: return "call not valid in the current state";
+    default: return "unknown error";
+  }
+}
+const char* chz_last_cuda_error(void) { return g_cuda_err.c_str(); }
+int chz_abi_version(void) { return CHZ_ABI_VERSION; }
+
+int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversample, chz_t** out) {
+  if (!out) return CHZ_EINVAL;
+  *out = nullptr;
+  if (M < 8 || M > 4096 || (M & (M - 1))) return CHZ_EINVAL;
+  if (oversample != 1 && oversample != 2) return CHZ_EINVAL;
+  if (taps && (ntaps == 0 || ntaps % M != 0 || ntaps / M > 32)) return CHZ_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return CHZ_ENODEVICE; }
+  int dev = 0;
+  CHZ_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CHZ_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return CHZ_ENODEVICE;   // kernels are built for sm_100a only
+  chz* h = new (std::nothrow) chz;
+  if (!h) return CHZ_ENOMEM;
+  h->device = dev;
+  h->sm_count = prop.multiProcessorCount;
+  h->M = M; h->os = oversample; h->D = M / oversample;
+  if (taps) {
+    h->taps.assign(taps, taps + ntaps);
+  } else {
+    h->taps.resize((size_t)M * 12);   // dsp.Channelizer defaults: 12 taps per band, 80 dB
+    chz_design_prototype(M, 12, 80.0, h->taps.data());
+  }
+  h->L = (uint32_t)h->taps.size();
+  h->P = h->L / M;
+  auto fail = [&](int rc) { chz_destroy(h); return rc; };
+#define CHZ_TRY(call) do { if ((call) != cudaSuccess) { set_cuda_error(cudaGetLastError(), #call, __FILE__, __LINE__); return fail(CHZ_ECUDA); } } while (0)
+  CHZ_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CHZ_TRY(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+  CHZ_TRY(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  for (int i = 0; i < 2; i++) {
+    CHZ_TRY(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+    CHZ_TRY(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+    CHZ_TRY(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+  }
+  std::vector<float2> tw(M);
+  for (uint32_t i = 0; i < M; i++) {
+    const double a = 2.0 * 3.14159265358979323846264338327950288 * (double)i / (double)M;
+    tw[i] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  CHZ_TRY(cudaMalloc(&h->d_tw, sizeof(float2) * M));
+  CHZ_TRY(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+  h->hist_cap = (uint64_t)h->L + h->D + 16;
+  for (int i = 0; i < 2; i++) {
+    CHZ_TRY(cudaMalloc(&h->d_hist[i], h->hist_cap * 4));
+    CHZ_TRY(cudaMemset(h->d_hist[i], 0, h->hist_cap * 4));
+  }
+#undef CHZ_TRY
+  *out = h;
+  return CHZ_OK;
+}
+
+void chz_destroy(chz_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  for (int i = 0; i < 17; i++) if (h->d_taps[i]) cudaFree(h->d_taps[i]);
+  if (h->d_tw) cudaFree(h->d_tw);
+  for (int i = 0; i < 2; i++) {
+    if (h->d_hist[i]) cudaFree(h->d_hist[i]);
+    if (h->d_in[i]) cudaFree(h->d_in[i]);
+    if (h->d_out[i]) cudaFree(h->d_out[i]);
+    if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+    if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+    if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+  }
+  if (h->d_store) cudaFree(h->d_store);
+  if (h->d_u) cudaFree(h->d_u);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+  if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+  delete h;
+}
+
+int chz_reset(chz_t* h) {
+  if (!h) return CHZ_EINVAL;
+  h->consumed = 0; h->rows_done = 0; h->bit_width = 0;
+  h->hist_base = 0; h->hist_len = 0;
+  h->store_rows = 0;
+  h->pdws.clear(); h->noise_floor.clear();
+  return CHZ_OK;
+}
+
+int chz_set_stream(chz_t* h, void* cuda_stream) {
+  if (!h) return CHZ_EINVAL;
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return CHZ_OK;
+}
+
+int chz_set_option(chz_t* h, int opt, int64_t value) {
+  if (!h) return CHZ_EINVAL;
+  switch (opt) {
+    case CHZ_OPT_RETAIN: h->retain = value != 0; return CHZ_OK;
+    case CHZ_OPT_CHUNK_ROWS: if (value < 0) return CHZ_EINVAL; h->chunk_rows = value; return CHZ_OK;
+    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 2) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
+    default: return CHZ_EINVAL;
+  }
+}
+
+uint32_t chz_num_channels(const chz_t* h) { return h ? h->M : 0; }
+uint32_t chz_num_taps(const chz_t* h) { return h ? h->L : 0; }
+uint32_t chz_decimation(const chz_t* h) { return h ? h->D : 0; }
+int chz_get_taps(const chz_t* h, float* taps, uint32_t cap) {
+  if (!h || !taps) return CHZ_EINVAL;
+  if (cap < h->L) return CHZ_ECAPACITY;
+  memcpy(taps, h->taps.data(), sizeof(float) * h->L);
+  return CHZ_OK;
+}
+uint64_t chz_rows_for(const chz_t* h, uint64_t nsamp) {
+  return h ? (h->consumed + nsamp) / h->D - h->rows_done : 0;
+}
+uint64_t chz_kernel_launches(const chz_t* h) { return h ? h->launches : 0; }
+
+double chz_channel_freq(const chz_t* h, uint32_t k, double fs) {
+  if (!h || k >= h->M) return NAN;
+  const double step = fs / (double)h->M;
+  return k < (h->M + 1) / 2 ? k * step : ((double)k - (double)h->M) * step;
+}
+
+int chz_process_dev(chz_t* h, const void* iq_dev, uint64_t nsamp, uint32_t bit_width, chz_cf32* out_dev,
+                    uint64_t out_cap_rows, uint64_t* nrows) {
+  if (!h || (!iq_dev && nsamp)) return CHZ_EINVAL;
+  int rc = check_stream_args(h, nsamp, bit_width);
+  if (rc) return rc;
+  const uint64_t need = chz_rows_for(h, nsamp);
+  if (nrows) *nrows = need;
+  if (need > out_cap_rows) return CHZ_ECAPACITY;
+  if (need && !out_dev) return CHZ_EINVAL;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  h->bit_width = bit_width;
+  return run_chunk(h, iq_dev, nsamp, bit_width, (float2*)out_dev, nrows, h->stream);
+}
+
+int chz_synchronize(chz_t* h) {
+  if (!h) return CHZ_EINVAL;
+  CHZ_CUDA(cudaStreamSynchronize(h->stream));
+  return CHZ_OK;
+}
+
+int chz_process(chz_t* h, const void* iq, uint64_t nsamp, uint32_t bit_width, chz_cf32* out,
+                uint64_t out_cap_rows, uint64_t* nrows) {
+  if (!h || (!iq && nsamp)) return CHZ_EINVAL;
+  int rc = check_stream_args(h, nsamp, bit_width);
+  if (rc) return rc;
+  const uint64_t need = chz_rows_for(h, nsamp);
+  if (nrows) *nrows = need;
+  if (out && need > out_cap_rows) return CHZ_ECAPACITY;
+  if (!out && !h->retain && need) return CHZ_EINVAL;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  h->bit_width = bit_width;
+  const size_t bps = bit_width > 8 ? 4 : 2;
+  const uint64_t D = h->D, M = h->M;
+  if (nsamp == 0) { if (nrows) *nrows = 0; return CHZ_OK; }
+  // chunk geometry: whole frames per chunk so each chunk yields a fixed number of rows
+  uint64_t crow = h->chunk_rows > 0 ? (uint64_t)h->chunk_rows : (8ULL << 20) / D;   // ~8 Mi samples
+  if (crow < 1) crow = 1;
+  const uint64_t csamp = crow * D;
+  if (h->in_cap_bytes < (csamp + D) * bps) {
+    for (int i = 0; i < 2; i++) {
+      if (h->d_in[i]) CHZ_CUDA(cudaFree(h->d_in[i]));
+      h->d_in[i] = nullptr;
+      CHZ_CUDA(cudaMalloc(&h->d_in[i], (csamp + D) * bps));
+    }
+    h->in_cap_bytes = (csamp + D) * bps;
+  }
+  if (h->retain) {
+    rc = ensure_store(h, h->store_rows + need);
+    if (rc) return rc;
+  } else if (h->out_cap_rows < crow + 2) {
+    for (int i = 0; i < 2; i++) {
+      if (h->d_out[i]) CHZ_CUDA(cudaFree(h->d_out[i]));
+      h->d_out[i] = nullptr;
+      CHZ_CUDA(cudaMalloc(&h->d_out[i], (crow + 2) * M * sizeof(float2)));
+    }
+    h->out_cap_rows = crow + 2;
+  }
+  cudaStream_t sc = h->stream;
+  uint64_t done = 0, rows_out = 0;
+  int c = 0;
+  // make the side streams wait for whatever is already queued on the compute stream
+  CHZ_CUDA(cudaEventRecord(h->ev_comp[0], sc));
+  CHZ_CUDA(cudaEventRecord(h->ev_comp[1], sc));
+  CHZ_CUDA(cudaEventRecord(h->ev_d2h[0], h->s_d2h));
+  CHZ_CUDA(cudaEventRecord(h->ev_d2h[1], h->s_d2h));
+  while (done < nsamp) {
+    const int b = c & 1;
+    const uint64_t n = (nsamp - done) < csamp ? (nsamp - done) : csamp;
+    // H2D of chunk c may start once the kernel that last read d_in[b] (chunk c-2) is done
+    CHZ_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));
+    if (n) CHZ_CUDA(cudaMemcpyAsync(h->d_in[b], (const char*)iq + done * bps, n * bps, cudaMemcpyHostToDevice, h->s_h2d));
+    CHZ_CUDA(cudaEventRecord(h->ev_h2d[b], h->s_h2d));
+    CHZ_CUDA(cudaStreamWaitEvent(sc, h->ev_h2d[b], 0));
+    float2* dst;
+    if (h->retain) dst = h->d_store + h->store_rows * M;
+    else { dst = h->d_out[b]; CHZ_CUDA(cudaStreamWaitEvent(sc, h->ev_d2h[b], 0)); }
+    uint64_t r = 0;
+    rc = run_chunk(h, h->d_in[b], n, bit_width, dst, &r, sc);
+    if (rc) return rc;
+    CHZ_CUDA(cudaEventRecord(h->ev_comp[b], sc));
+    if (h->retain) h->store_rows += r;
+    if (out && r) {
+      CHZ_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
+      CHZ_CUDA(cudaMemcpyAsync(out + rows_out * M, dst, r * M * sizeof(float2), cudaMemcpyDeviceToHost, h->s_d2h));
+      CHZ_CUDA(cudaEventRecord(h->ev_d2h[b], h->s_d2h));
+    }
+    rows_out += r;
+    done += n;
+    c++;
+  }
+  CHZ_CUDA(cudaStreamSynchronize(h->s_h2d));
+  CHZ_CUDA(cudaStreamSynchronize(sc));
+  CHZ_CUDA(cudaStreamSynchronize(h->s_d2h));
+  if (nrows) *nrows = rows_out;
+  return CHZ_OK;
+}
+
+int chz_unpack_dev(const void* iq_dev, uint64_t nsamp, uint32_t bit_width, chz_cf32* out_dev, void* cuda_stream) {
+  if ((!iq_dev || !out_dev) && nsamp) return CHZ_EINVAL;
+  if (bit_width == 0 || bit_width > 16) return CHZ_EBITWIDTH;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return CHZ_ENODEVICE; }
+  if (!nsamp) return CHZ_OK;
+  const float scale = std::ldexp(1.0f, -(int)(bit_width - 1));
+  long long blocks = ((long long)nsamp + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (bit_width > 8) k_unpack<true><<<(unsigned)blocks, 256, 0, st>>>(iq_dev, (long long)nsamp, scale, (float2*)out_dev);
+  else k_unpack<false><<<(unsigned)blocks, 256, 0, st>>>(iq_dev, (long long)nsamp, scale, (float2*)out_dev);
+  CHZ_CUDA(cudaGetLastError());
+  return CHZ_OK;
+}
+
+int chz_fft_rows_dev(chz_t* h, const chz_cf32* u_dev, chz_cf32* y_dev, uint64_t nrows) {
+  if (!h || ((!u_dev || !y_dev) && nrows)) return CHZ_EINVAL;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  return launch_fft_rows(h, (const float2*)u_dev, (float2*)y_dev, (long long)nrows, h->stream);
+}
+
+int chz_retained(const chz_t* h, const chz_cf32** y_dev, uint64_t* nrows) {
+  if (!h) return CHZ_EINVAL;
+  if (y_dev) *y_dev = (const chz_cf32*)h->d_store;
+  if (nrows) *nrows = h->store_rows;
+  return CHZ_OK;
+}
+
+int chz_reserve_rows(chz_t* h, uint64_t nrows) {
+  if (!h) return CHZ_EINVAL;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  return ensure_store(h, nrows);
+}
+
+int chz_pdws_dev(chz_t* h, const chz_pdw_params_t* params, const chz_cf32* y_dev, uint64_t nrows,
+                 chz_pdw_t* out, uint64_t cap, uint64_t* n) {
+  if (!h || !params || (!y_dev && nrows)) return CHZ_EINVAL;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  const int rc = pdw_extract(h, params, (const float2*)y_dev, nrows);
+  if (rc) return rc;
+  if (n) *n = h->pdws.size();
+  if (h->pdws.size() > cap) return CHZ_ECAPACITY;
+  if (out && !h->pdws.empty()) memcpy(out, h->pdws.data(), h->pdws.size() * sizeof(chz_pdw_t));
+  return CHZ_OK;
+}
+
+int chz_pdws(chz_t* h, const chz_pdw_params_t* params, chz_pdw_t* out, uint64_t cap, uint64_t* n) {
+  if (!h) return CHZ_EINVAL;
+  if (!h->retain) return CHZ_ESTATE;
+  return chz_pdws_dev(h, params, (const chz_cf32*)h->d_store, h->store_rows, out, cap, n);
+}
+
+int chz_pdws_fetch(const chz_t* h, chz_pdw_t* out, uint64_t cap, uint64_t* n) {
+  if (!h) return CHZ_EINVAL;
+  if (n) *n = h->pdws.size();
+  if (h->pdws.size() > cap) return CHZ_ECAPACITY;
+  if (out && !h->pdws.empty()) memcpy(out, h->pdws.data(), h->pdws.size() * sizeof(chz_pdw_t));
+  return CHZ_OK;
+}
+
+int chz_pdw_noise_floor(const chz_t* h, double* nf, uint32_t cap) {
+  if (!h || !nf) return CHZ_EINVAL;
+  if (h->noise_floor.size() != h->M) return CHZ_ESTATE;
+  if (cap < h->M) return CHZ_ECAPACITY;
+  memcpy(nf, h->noise_floor.data(), sizeof(double) * h->M);
+  return CHZ_OK;
+}
+
+void* chz_alloc_host(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void chz_free_host(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,179 @@
+// Device-side building blocks shared by the channelizer kernels (sm_100a only).
+//   K1  raw int8/int16 I/Q -> fp32 (exact; matlab/create_pdws_channelized.m:35-38)
+//   K3  in-register DFT-2/4/8/16 and the shared-memory Stockham FFT over polyphase branches
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace chzi {
+
+// ---- complex helpers (float2 = re,im).  __f*2_rn map to the packed FADD2/FMUL2/FFMA2 of sm_100 ----
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {   // a*w
+  return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+}
+__device__ __forceinline__ float2 mul_j(float2 a) { return make_float2(-a.y, a.x); }    // * (+j)
+
+// ---- K1: exact integer -> float without I2F (which runs on the quarter-rate conversion pipe) ------
+// 0x4B000000 | u  is the float 2^23 + u for u < 2^23; XOR with the sign bit turns two's complement
+// into offset binary, so (2^23 + (v ^ signbit)) - (2^23 + bias) == v exactly.
+template <bool IN16> struct RawT;
+template <> struct RawT<true> { typedef uint32_t type; };    // int16 I, int16 Q
+template <> struct RawT<false> { typedef uint16_t type; };   // int8 I, int8 Q
+
+template <bool IN16>
+__device__ __forceinline__ float2 unpack_raw(uint32_t raw) {   // integer-valued, NOT yet scaled
+  if (IN16) {
+    const uint32_t t = raw ^ 0x80008000u;
+    const float2 f = make_float2(__uint_as_float(__byte_perm(t, 0x4B000000u, 0x7610)),
+                                 __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7632)));
+    return __fadd2_rn(f, make_float2(-8421376.0f, -8421376.0f));   // 2^23 + 2^15
+  } else {
+    const uint32_t t = raw ^ 0x8080u;
+    const float2 f = make_float2(__uint_as_float(__byte_perm(t, 0x4B000000u, 0x7640)),
+                                 __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7641)));
+    return __fadd2_rn(f, make_float2(-8388736.0f, -8388736.0f));   // 2^23 + 2^7
+  }
+}
+
+// ---- in-register DFTs, exponent +j (y_t = sum_s v_s e^{+j 2 pi s t / R}), natural order in/out ----
+__device__ __forceinline__ void dft2(float2& a, float2& b) {
+  const float2 t = csub(a, b);
+  a = cadd(a, b);
+  b = t;
+}
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_j(csub(a1, a3));
+  a0 = cadd(t0, t2); a1 = cadd(t1, t3); a2 = csub(t0, t2); a3 = csub(t1, t3);
+}
+__device__ __forceinline__ void dft8(float2* v) {
+  // DIT: E = DFT4(v0,v2,v4,v6), O = DFT4(v1,v3,v5,v7); X[k] = E[k] + W8^k O[k], X[k+4] = E[k] - W8^k O[k]
+  dft4(v[0], v[2], v[4], v[6]);
+  dft4(v[1], v[3], v[5], v[7]);
+  const float c = 0.70710678118654752440f;
+  const float2 o1 = make_float2(c * (v[3].x - v[3].y), c * (v[3].x + v[3].y));     // W8^1 = (1+j)/sqrt2
+  const float2 o2 = mul_j(v[5]);                                                   // W8^2 = j
+  const float2 o3 = make_float2(-c * (v[7].x + v[7].y), c * (v[7].x - v[7].y));    // W8^3 = (-1+j)/sqrt2
+  const float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+__device__ __forceinline__ void dft16(float2* v) {
+  // n = 4 n1 + n2, k = k1 + 4 k2:  A[n2][k1] = DFT4 over n1; twiddle W16^{n2 k1}; DFT4 over n2.
+  #pragma unroll
+  for (int n2 = 0; n2 < 4; n2++) dft4(v[n2], v[n2 + 4], v[n2 + 8], v[n2 + 12]);   // v[n2 + 4 k1] = A[n2][k1]
+  const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, c2 = 0.70710678118654752440f;
+  // k1 = 1: W16^{n2}, n2 = 1,2,3
+  v[5] = cmul(v[5], make_float2(c1, s1));
+  v[6] = cmul(v[6], make_float2(c2, c2));
+  v[7] = cmul(v[7], make_float2(s1, c1));
+  // k1 = 2: W16^{2 n2} = W8^{n2}
+  v[9] = cmul(v[9], make_float2(c2, c2));
+  v[10] = mul_j(v[10]);
+  v[11] = cmul(v[11], make_float2(-c2, c2));
+  // k1 = 3: W16^{3 n2}
+  v[13] = cmul(v[13], make_float2(s1, c1));
+  v[14] = cmul(v[14], make_float2(-c2, c2));
+  v[15] = cmul(v[15], make_float2(-c1, -s1));
+  #pragma unroll
+  for (int k1 = 0; k1 < 4; k1++) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);  // -> X[k1 + 4 k2] at v[4 k1 + k2]
+  // reorder to natural k = k1 + 4 k2  (register renaming, no data movement after unrolling)
+  float2 t[16];
+  #pragma unroll
+  for (int k1 = 0; k1 < 4; k1++)
+    #pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) t[k1 + 4 * k2] = v[4 * k1 + k2];
+  #pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = t[i];
+}
+template <int R> __device__ __forceinline__ void dft(float2* v);
+template <> __device__ __forceinline__ void dft<2>(float2* v) { dft2(v[0], v[1]); }
+template <> __device__ __forceinline__ void dft<4>(float2* v) { dft4(v[0], v[1], v[2], v[3]); }
+template <> __device__ __forceinline__ void dft<8>(float2* v) { dft8(v); }
+template <> __device__ __forceinline__ void dft<16>(float2* v) { dft16(v); }
+
+// ---- FFT plan: radices per pass.  First pass radix is 16 or 8 so that every later Stockham pass
+// writes runs of >= 16 contiguous elements (bank-conflict-free), see DESIGN.md. -----------------------
+template <int M> struct Plan;
+template <> struct Plan<8>    { static constexpr int np = 1; static constexpr int r0 = 8,  r1 = 1,  r2 = 1; };
+template <> struct Plan<16>   { static constexpr int np = 1; static constexpr int r0 = 16, r1 = 1,  r2 = 1; };
+template <> struct Plan<32>   { static constexpr int np = 2; static constexpr int r0 = 8,  r1 = 4,  r2 = 1; };
+template <> struct Plan<64>   { static constexpr int np = 2; static constexpr int r0 = 8,  r1 = 8,  r2 = 1; };
+template <> struct Plan<128>  { static constexpr int np = 2; static constexpr int r0 = 16, r1 = 8,  r2 = 1; };
+template <> struct Plan<256>  { static constexpr int np = 2; static constexpr int r0 = 16, r1 = 16, r2 = 1; };
+template <> struct Plan<512>  { static constexpr int np = 3; static constexpr int r0 = 16, r1 = 8,  r2 = 4; };
+template <> struct Plan<1024> { static constexpr int np = 3; static constexpr int r0 = 16, r1 = 8,  r2 = 8; };
+template <> struct Plan<2048> { static constexpr int np = 3; static constexpr int r0 = 16, r1 = 16, r2 = 8; };
+template <> struct Plan<4096> { static constexpr int np = 3; static constexpr int r0 = 16, r1 = 16, r2 = 16; };
+
+// Padded element index inside one row of the shared tile (8-byte elements): one pad element per 16.
+__device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
+template <int M> struct RowStride { static constexpr int value = M + M / 16 + (M < 16 ? 1 : 0); };
+
+// One Stockham pass of radix R over `rows` rows of length M held in shared memory.
+//   src/dst : [rows][RowStride<M>] float2 (padded with padi)
+//   Ns      : product of the radices of earlier passes
+//   LAST    : write to global memory (gout + row*grow_stride + k) instead of dst; rows >= vrows skipped
+// Threads `t` of `nt` cooperate; consecutive threads take consecutive butterflies of a row.
+template <int M, int R, bool LAST>
+__device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, float2* __restrict__ dst,
+                                              const float2* __restrict__ tw, int Ns, int rows, int t, int nt,
+                                              float2* __restrict__ gout, long long grow_stride, int vrows) {
+  constexpr int S = RowStride<M>::value;
+  constexpr int BPR = M / R;   // butterflies per row
+  const int total = rows * BPR;
+  for (int b = t; b < total; b += nt) {
+    const int row = b / BPR, j = b - row * BPR;
+    const float2* s = src + row * S;
+    float2 v[R];
+    #pragma unroll
+    for (int q = 0; q < R; q++) v[q] = s[padi(j + q * BPR)];
+    const int k = j & (Ns - 1);   // j mod Ns (Ns is a power of two)
+    if (Ns > 1) {
+      const int tstep = (M / R) / Ns;   // table stride: W_{Ns R}^{q k} = W_M^{q k M/(Ns R)}
+      #pragma unroll
+      for (int q = 1; q < R; q++) v[q] = cmul(v[q], tw[q * k * tstep]);
+    }
+    dft<R>(v);
+    const int j0 = (j - k) * R + k;   // (j / Ns) * Ns * R + k
+    if (LAST) {
+      if (row < vrows) {
+        float2* g = gout + (long long)row * grow_stride;
+        #pragma unroll
+        for (int q = 0; q < R; q++) g[j0 + q * Ns] = v[q];
+      }
+    } else {
+      float2* d = dst + row * S;
+      #pragma unroll
+      for (int q = 0; q < R; q++) d[padi(j0 + q * Ns)] = v[q];
+    }
+  }
+}
+
+// Full M-point FFT (exponent +j) of `rows` rows.  buf0 holds the input (padded layout); buf1 is
+// scratch of the same size.  Result goes to global memory in natural order.  `sync()` must
+// synchronise exactly the threads that cooperate on this tile.
+template <int M, typename SyncF>
+__device__ __forceinline__ void fft_tile_to_global(float2* buf0, float2* buf1, const float2* tw, int rows, int t,
+                                                   int nt, float2* gout, long long grow_stride, int vrows,
+                                                   SyncF sync) {
+  typedef Plan<M> PL;
+  if constexpr (PL::np == 1) {
+    stockham_pass<M, PL::r0, true>(buf0, buf1, tw, 1, rows, t, nt, gout, grow_stride, vrows);
+  } else if constexpr (PL::np == 2) {
+    stockham_pass<M, PL::r0, false>(buf0, buf1, tw, 1, rows, t, nt, gout, grow_stride, vrows);
+    sync();
+    stockham_pass<M, PL::r1, true>(buf1, buf0, tw, PL::r0, rows, t, nt, gout, grow_stride, vrows);
+  } else {
+    stockham_pass<M, PL::r0, false>(buf0, buf1, tw, 1, rows, t, nt, gout, grow_stride, vrows);
+    sync();
+    stockham_pass<M, PL::r1, false>(buf1, buf0, tw, PL::r0, rows, t, nt, gout, grow_stride, vrows);
+    sync();
+    stockham_pass<M, PL::r2, true>(buf0, buf1, tw, PL::r0 * PL::r1, rows, t, nt, gout, grow_stride, vrows);
+  }
+}
+
+}  // namespace chzi

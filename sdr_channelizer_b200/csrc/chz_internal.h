@@ -1,0 +1,71 @@
+// Internal state of a channelizer handle (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "channelizer.h"
+
+namespace chzi {
+
+void set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
+
+#define CHZ_CUDA(call)                                                  \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) {                                           \
+      ::chzi::set_cuda_error(e__, #call, __FILE__, __LINE__);            \
+      return CHZ_ECUDA;                                                 \
+    }                                                                   \
+  } while (0)
+
+}  // namespace chzi
+
+struct chz {
+  int device = 0;
+  int sm_count = 148;
+  uint32_t M = 0, P = 0, L = 0, os = 1, D = 0;
+  std::vector<float> taps;              // prototype as given (unscaled), h[qM + p]
+  float* d_taps[17] = {nullptr};        // per bit width: taps * 2^-(bw-1), uploaded on first use
+  float2* d_tw = nullptr;               // e^{+j 2 pi i / M}
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+
+  // streaming state (stream indices count complex samples since reset)
+  uint64_t consumed = 0, rows_done = 0;
+  uint32_t bit_width = 0;               // of the current stream (0 = none yet)
+  void* d_hist[2] = {nullptr, nullptr};
+  int hist_cur = 0;
+  uint64_t hist_base = 0, hist_len = 0, hist_cap = 0;   // samples
+
+  // retained channel output (for chz_pdws)
+  bool retain = true;
+  float2* d_store = nullptr;
+  uint64_t store_rows = 0, store_cap = 0;
+
+  // split-path scratch (FIR output rows)
+  float2* d_u = nullptr;
+  uint64_t u_cap_rows = 0;
+
+  // host-path staging
+  void* d_in[2] = {nullptr, nullptr};
+  uint64_t in_cap_bytes = 0;
+  float2* d_out[2] = {nullptr, nullptr};
+  uint64_t out_cap_rows = 0;
+  int64_t chunk_rows = 0;
+
+  int force_path = 0;
+  uint64_t launches = 0;
+
+  // PDW results of the last run
+  std::vector<double> noise_floor;      // natural channel order
+  std::vector<chz_pdw_t> pdws;
+};
+
+namespace chzi {
+// pdw.cu
+int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y_dev, uint64_t nrows);
+}  // namespace chzi

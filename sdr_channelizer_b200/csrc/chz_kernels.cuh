@@ -1,0 +1,227 @@
+// Channelizer kernels (K1 unpack, K2 polyphase FIR, K3 FFT, and the fused K1+K2+K3), sm_100a.
+// Reference math replaced: matlab/create_pdws_channelized.m:35-38 (normalise) and :57
+// (iq = channelizer(iq), MathWorks dsp.Channelizer — closed source; definition in DESIGN.md).
+#pragma once
+#include "chz_device.cuh"
+
+namespace chzi {
+
+// Everything a launch needs to know about where stream sample `idx` lives and which rows to make.
+// Stream indices count complex samples since the last reset.  Row m's newest sample is m*D and it is
+// produced once the whole frame [m*D, m*D + D) has arrived.
+struct ChanParams {
+  const void* in;        // raw samples of this call: stream indices [in_base, in_base + n_in)
+  const void* hist;      // raw history: stream indices [hist_base, in_base)
+  long long in_base, n_in, hist_base;
+  const float* taps;     // [P][M], already multiplied by 2^-(bit_width-1) (exact)
+  const float2* tw;      // W_M^i = e^{+j 2 pi i / M}, i < M
+  float2* out;           // row `row_base` starts at out[0]; row-major [row][M]
+  long long row_base;    // first stream row produced by this call
+  long long nrows;       // rows produced by this call
+  int M, D, os;          // os = M / D (1 or 2)
+  int span_rows;         // rows of one phase handled between window warm-ups (multiple of P)
+  long long spans_per_phase;
+};
+
+// Raw word of stream sample idx; 0 (which unpacks to 0+0j) outside what has been received:
+// x[n < 0] = 0, and rows past the end of a partial tile are computed but never stored.
+template <bool IN16>
+__device__ __forceinline__ uint32_t load_raw(const ChanParams& p, long long idx) {
+  typedef typename RawT<IN16>::type raw_t;
+  if (idx >= p.in_base) {
+    if (idx < p.in_base + p.n_in) return __ldg((const raw_t*)p.in + (idx - p.in_base));
+    return 0u;
+  }
+  if (idx >= p.hist_base) return __ldg((const raw_t*)p.hist + (idx - p.hist_base));
+  return 0u;
+}
+
+// ---- K1 stand-alone: raw -> complex fp32, bit exact (create_pdws_channelized.m:35-38) ------------
+template <bool IN16>
+__global__ void k_unpack(const void* __restrict__ in, long long n, float scale, float2* __restrict__ out) {
+  typedef typename RawT<IN16>::type raw_t;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float2 v = unpack_raw<IN16>(__ldg((const raw_t*)in + i));
+    out[i] = make_float2(v.x * scale, v.y * scale);   // power-of-two scale: exact
+  }
+}
+
+// Describes the span a thread group works on.
+struct Span {
+  long long m0;      // first stream row of the span
+  long long count;   // rows in the span (stride `os` rows apart)
+  int shift;         // (m*D) mod M, the circular branch rotation of these rows (0 or M/2)
+};
+__device__ __forceinline__ Span make_span(const ChanParams& p, long long sp) {
+  Span s;
+  const int phase_i = (int)(sp % p.os);          // which residue class of rows (relative to row_base)
+  const long long si = sp / p.os;
+  const long long first = p.row_base + phase_i;   // first row of this class
+  const long long cnt_phase = (p.nrows - phase_i + p.os - 1) / p.os;
+  const long long i0 = si * (long long)p.span_rows;
+  s.m0 = first + i0 * p.os;
+  s.count = cnt_phase - i0;
+  if (s.count > p.span_rows) s.count = p.span_rows;
+  if (s.count < 0) s.count = 0;
+  s.shift = (int)((s.m0 * p.D) % p.M);
+  return s;
+}
+
+// ---- K2: polyphase FIR commutator, one thread per branch, sliding window in registers --------------
+// u_p[m] = sum_q h[qM+p] x[mD - qM - p].  The P taps of a branch and its last P samples live in
+// registers; a new row costs one 4-byte (int16) or 2-byte (int8) coalesced load and P packed FMAs
+// (fma.rn.f32x2 on (re,im) with the tap duplicated).  `emit(i, value)` receives row i of the span.
+template <int P, bool IN16, typename Emit>
+__device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, int p, Emit emit) {
+  typedef typename RawT<IN16>::type raw_t;
+  float2 hh[P], w[P];
+  #pragma unroll
+  for (int q = 0; q < P; q++) { const float h = __ldg(prm.taps + q * prm.M + p); hh[q] = make_float2(h, h); }
+  const long long base = sp.m0 * prm.D - p;   // newest sample of span row 0 for this branch
+  const long long Ml = prm.M;
+  const long long in_end = prm.in_base + prm.n_in;
+  const raw_t* __restrict__ inp = (const raw_t*)prm.in - prm.in_base;   // inp[idx] for idx in [in_base, in_end)
+  // warm-up: rows -(P-1)..-1 go to slots 1..P-1 (row -k -> slot P-k)
+  w[0] = make_float2(0.f, 0.f);
+  #pragma unroll
+  for (int k = 1; k < P; k++) w[P - k] = unpack_raw<IN16>(load_raw<IN16>(prm, base - k * Ml));
+  for (long long i0 = 0; i0 < sp.count; i0 += P) {
+    uint32_t raw[P];
+    const long long lo = base + i0 * Ml;
+    if (lo >= prm.in_base && lo + (P - 1) * Ml < in_end) {   // interior tile: plain coalesced loads
+      #pragma unroll
+      for (int ii = 0; ii < P; ii++) raw[ii] = __ldg(inp + (lo + ii * Ml));
+    } else {
+      #pragma unroll
+      for (int ii = 0; ii < P; ii++) raw[ii] = load_raw<IN16>(prm, lo + ii * Ml);
+    }
+    #pragma unroll
+    for (int ii = 0; ii < P; ii++) {
+      w[ii] = unpack_raw<IN16>(raw[ii]);
+      float2 acc = __fmul2_rn(hh[0], w[ii]);
+      #pragma unroll
+      for (int q = 1; q < P; q++) acc = __ffma2_rn(hh[q], w[(ii - q + P) % P], acc);
+      emit((int)ii, i0 + ii, acc);
+    }
+  }
+}
+
+// Split path, kernel A: FIR only, u rows to global memory (already circularly rotated).
+// grid.x = branch blocks * span blocks; block = 128 threads.
+template <int P, bool IN16>
+__global__ void __launch_bounds__(128) k_fir(ChanParams prm, float2* __restrict__ u) {
+  const int bpb = prm.M < 128 ? prm.M : 128;       // branches per block
+  const int nbb = prm.M / bpb;                     // branch blocks
+  const int groups = 128 / bpb;                    // spans handled side by side in one block
+  const int bb = blockIdx.x % nbb, g = threadIdx.x / bpb;
+  const int p = bb * bpb + threadIdx.x % bpb;
+  const long long nspans = prm.spans_per_phase * prm.os;
+  const long long sstride = (long long)(gridDim.x / nbb) * groups;
+  for (long long s = (long long)(blockIdx.x / nbb) * groups + g; s < nspans; s += sstride) {
+    const Span sp = make_span(prm, s);
+    if (sp.count <= 0) continue;
+    const int r = (p - sp.shift + prm.M) % prm.M;   // u'[r] = u[(r + shift) mod M]
+    float2* dst = u + (sp.m0 - prm.row_base) * (long long)prm.M + r;
+    const long long rstride = (long long)prm.os * prm.M;
+    fir_span<P, IN16>(prm, sp, p, [&](int, long long i, float2 v) {
+      if (i < sp.count) dst[i * rstride] = v;
+    });
+  }
+}
+
+// Split path, kernel A for tap counts without a register-window instantiation: direct evaluation,
+// P loads per output (slow; correctness fallback only).
+template <bool IN16>
+__global__ void k_fir_any(ChanParams prm, int P, float2* __restrict__ u) {
+  const long long total = prm.nrows * prm.M;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long row = e / prm.M;
+    const int p = (int)(e - row * prm.M);
+    const long long m = prm.row_base + row, t = m * prm.D;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int q = 0; q < P; q++) {
+      const float h = __ldg(prm.taps + q * prm.M + p);
+      acc = __ffma2_rn(make_float2(h, h), unpack_raw<IN16>(load_raw<IN16>(prm, t - (long long)q * prm.M - p)), acc);
+    }
+    const int shift = (int)(t % prm.M);
+    u[row * prm.M + (p - shift + prm.M) % prm.M] = acc;
+  }
+}
+
+// Split path, kernel B (also K3 on its own): M-point FFT of rows in global memory.
+// One block transforms ROWS rows at a time.  Dynamic smem: 2 * ROWS * RowStride<M> float2 + M float2.
+template <int M, int ROWS, int NT>
+__global__ void __launch_bounds__(NT) k_fft_rows(const float2* __restrict__ u, float2* __restrict__ y,
+                                                 const float2* __restrict__ tw_g, long long nrows) {
+  extern __shared__ float2 smem[];
+  constexpr int S = RowStride<M>::value;
+  float2* buf0 = smem;
+  float2* buf1 = buf0 + ROWS * S;
+  float2* tw = buf1 + ROWS * S;
+  for (int i = threadIdx.x; i < M; i += NT) tw[i] = tw_g[i];
+  for (long long r0 = (long long)blockIdx.x * ROWS; r0 < nrows; r0 += (long long)gridDim.x * ROWS) {
+    const int vrows = (int)((nrows - r0) < ROWS ? (nrows - r0) : ROWS);
+    __syncthreads();
+    for (int e = threadIdx.x; e < ROWS * M; e += NT) {
+      const int row = e / M, i = e - row * M;
+      buf0[row * S + padi(i)] = row < vrows ? u[(r0 + row) * M + i] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    fft_tile_to_global<M>(buf0, buf1, tw, ROWS, threadIdx.x, NT, y + r0 * M, (long long)M, vrows,
+                          [] { __syncthreads(); });
+  }
+}
+
+// ---- fused K1+K2+K3: one global read (raw int samples), one global write (fp32 channels) ----------
+// A block is G groups of M threads; a group walks spans of rows.  Every RT filtered rows (RT divides
+// P) the group runs the M-point FFT on its shared tile and streams the result to global memory.
+template <int M, int P> struct FusedCfg {
+  static constexpr int NT = M < 256 ? 256 : M;       // threads per block
+  static constexpr int G = NT / M;                   // groups per block
+  // rows per FFT tile: largest divisor of P keeping the two tile buffers of a block under ~72 KB
+  static constexpr int RTMAX = (72 * 1024) / (2 * 8 * RowStride<M>::value * G);
+  static constexpr int RT = RTMAX >= P ? P : (P % 8 == 0 && RTMAX >= 8 ? 8 : (P % 6 == 0 && RTMAX >= 6 ? 6 : (P % 4 == 0 && RTMAX >= 4 ? 4 : (P % 2 == 0 && RTMAX >= 2 ? 2 : 1))));
+  static constexpr size_t SMEM = (size_t)(M + G * 2 * RT * RowStride<M>::value) * sizeof(float2);
+};
+
+template <int M> __device__ __forceinline__ void group_sync(int g) {
+  if (M >= 64) asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(M) : "memory");   // named barrier per group
+  else __syncwarp();   // M <= 32: a group lives inside one warp
+}
+
+template <int M, int P, bool IN16>
+__global__ void __launch_bounds__(FusedCfg<M, P>::NT) k_chan_fused(ChanParams prm) {
+  extern __shared__ float2 smem[];
+  typedef FusedCfg<M, P> CF;
+  constexpr int NT = CF::NT, G = CF::G, RT = CF::RT, S = RowStride<M>::value;
+  float2* tw = smem;                                  // M twiddles
+  const int g = threadIdx.x / M, p = threadIdx.x % M;
+  float2* buf0 = smem + M + (size_t)g * 2 * RT * S;   // [RT][S]
+  float2* buf1 = buf0 + RT * S;
+  for (int i = threadIdx.x; i < M; i += NT) tw[i] = prm.tw[i];
+  __syncthreads();
+  const long long nspans = prm.spans_per_phase * prm.os;
+  const long long rstride = (long long)prm.os * M;
+  for (long long s = (long long)blockIdx.x * G + g; s < nspans; s += (long long)gridDim.x * G) {
+    const Span sp = make_span(prm, s);
+    if (sp.count <= 0) continue;                      // the whole group takes the same branch
+    const int r = padi((p - sp.shift + M) % M);
+    float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
+    fir_span<P, IN16>(prm, sp, p, [&](int ii, long long i, float2 v) {
+      buf0[(ii % RT) * S + r] = v;
+      if (ii % RT == RT - 1) {
+        group_sync<M>(g);
+        const long long i0 = i - (RT - 1);
+        const long long left = sp.count - i0;
+        const int vrows = (int)(left < RT ? (left < 0 ? 0 : left) : RT);
+        fft_tile_to_global<M>(buf0, buf1, tw, RT, p, M, gout + i0 * rstride, rstride, vrows,
+                              [&] { group_sync<M>(g); });
+        if (Plan<M>::np != 2) group_sync<M>(g);   // the last pass of 1- and 3-pass plans reads buf0
+      }
+    });
+  }
+}
+
+}  // namespace chzi

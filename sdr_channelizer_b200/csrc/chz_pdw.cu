@@ -1,0 +1,394 @@
+// K4: channelized PDW extraction on the GPU.
+// Replaces matlab/create_pdws_channelized.m:60-136:
+//   :60      fftshift            -> channel index remap when records are built (no data movement)
+//   :67      mag = abs(iq)       -> mag_of() recomputed from the fp32 channel matrix in every pass
+//   :73      median(mag)         -> exact per-channel radix select (3 histogram passes, 11+11+9 bits)
+//   :75      threshold           -> host, double precision, then bracketed by two floats
+//   :79-96   edge FSM            -> k_detect: lanes = channels (coalesced), rows in lock-step, warp
+//                                   ballot + one atomic per warp to compact edge events
+//   :97-128  per-pulse stats     -> k_pulse_stats: one block per pulse, radix-select medians
+// Input layout: y[row][k], natural channel order, fp32 complex.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "chz_internal.h"
+
+namespace chzi {
+
+__device__ __forceinline__ float mag_of(float2 v) {   // |y| in fp32, one rounding sequence everywhere
+  return __fsqrt_rn(__fmaf_rn(v.x, v.x, __fmul_rn(v.y, v.y)));
+}
+
+// ---- exact per-channel median: radix select over the bit pattern of non-negative floats ------------
+constexpr int kBins = 2048;
+struct SelState {          // per channel, two order statistics (lower and upper middle element)
+  uint32_t prefix[2];      // bits fixed so far (high bits)
+  uint32_t rank[2];        // rank still to find inside the prefix bucket
+};
+
+// pass 0: bits 30..20, pass 1: bits 19..9, pass 2: bits 8..0
+__device__ __forceinline__ int pass_shift(int pass) { return pass == 0 ? 20 : (pass == 1 ? 9 : 0); }
+__device__ __forceinline__ uint32_t pass_mask(int pass) { return pass == 2 ? 0x1FFu : 0x7FFu; }
+__device__ __forceinline__ uint32_t prefix_mask(int pass) { return pass == 0 ? 0u : (pass == 1 ? 0xFFF00000u : 0xFFFFFE00u); }
+
+// grid: (channel groups of 4, row chunks).  block 256 = 64 rows x 4 channels per step (32-byte row
+// segments, i.e. whole DRAM sectors).
+// hist: [M][2][kBins] uint32.  Slot 0 is privatised in shared memory; slot 1 (only used when the two
+// order statistics have diverged into different buckets) goes straight to global atomics.
+__global__ void __launch_bounds__(256) k_hist(const float2* __restrict__ y, long long nrows, int M, int pass,
+                                              const SelState* __restrict__ st, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[4 * kBins];
+  for (int i = threadIdx.x; i < 4 * kBins; i += 256) sh[i] = 0;
+  const int cl = threadIdx.x & 3, ch = blockIdx.x * 4 + cl;
+  const int shift = pass_shift(pass);
+  const uint32_t bmask = pass_mask(pass), pmask = prefix_mask(pass);
+  uint32_t p0 = 0, p1 = 0;
+  if (pass > 0) { p0 = st[ch].prefix[0]; p1 = st[ch].prefix[1]; }
+  const bool split = p0 != p1;
+  __syncthreads();
+  const long long rows_per_block = (nrows + gridDim.y - 1) / gridDim.y;
+  const long long r_begin = (long long)blockIdx.y * rows_per_block;
+  long long r_end = r_begin + rows_per_block;
+  if (r_end > nrows) r_end = nrows;
+  for (long long r = r_begin + (threadIdx.x >> 2); r < r_end; r += 64) {
+    const uint32_t bits = __float_as_uint(mag_of(y[r * M + ch]));
+    const uint32_t pre = bits & pmask, bin = (bits >> shift) & bmask;
+    if (pre == p0) atomicAdd(&sh[cl * kBins + bin], 1u);
+    if (split && pre == p1) atomicAdd(&hist[((size_t)ch * 2 + 1) * kBins + bin], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * kBins; i += 256) {
+    const uint32_t v = sh[i];
+    if (v) atomicAdd(&hist[((size_t)(blockIdx.x * 4 + i / kBins) * 2) * kBins + (i % kBins)], v);
+  }
+}
+
+// one block per channel: find the bucket holding each wanted rank, fix its bits, reduce the rank
+__global__ void __launch_bounds__(256) k_select(uint32_t* __restrict__ hist, SelState* __restrict__ st, int pass,
+                                                uint32_t rank_lo, uint32_t rank_hi) {
+  __shared__ uint32_t part[256];
+  __shared__ uint32_t res_bin[2], res_rank[2];
+  const int ch = blockIdx.x;
+  SelState s;
+  if (pass == 0) { s.prefix[0] = s.prefix[1] = 0; s.rank[0] = rank_lo; s.rank[1] = rank_hi; }
+  else s = st[ch];
+  const bool split = pass > 0 && s.prefix[0] != s.prefix[1];
+  const int nb = pass == 2 ? 512 : kBins, per = nb / 256;
+  for (int slot = 0; slot < 2; slot++) {
+    uint32_t* hrow = hist + ((size_t)ch * 2 + ((slot == 1 && split) ? 1 : 0)) * kBins;
+    uint32_t loc = 0;
+    for (int i = 0; i < per; i++) loc += hrow[threadIdx.x * per + i];
+    part[threadIdx.x] = loc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0, want = s.rank[slot];
+      int t = 0;
+      for (; t < 255; t++) { if (acc + part[t] > want) break; acc += part[t]; }
+      int b = t * per;
+      for (; b < t * per + per - 1; b++) { if (acc + hrow[b] > want) break; acc += hrow[b]; }
+      res_bin[slot] = (uint32_t)b;
+      res_rank[slot] = want - acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
+    for (int slot = 0; slot < 2; slot++) { s.prefix[slot] |= res_bin[slot] << shift; s.rank[slot] = res_rank[slot]; }
+    st[ch] = s;
+  }
+  __syncthreads();
+  // clear both histogram rows of this channel for the next pass
+  for (int i = threadIdx.x; i < 2 * kBins; i += 256) hist[(size_t)ch * 2 * kBins + i] = 0;
+}
+
+// ---- edge detection -----------------------------------------------------------------------------------
+struct Thr { float ge, le; };   // mag >= thr  <=>  mag >= ge ;  mag <= thr  <=>  mag <= le  (thr is a double)
+
+// Lanes walk channels (coalesced 8-byte loads of a row), all lanes advance row by row through the same
+// chunk, so a warp ballot per row tells whether any channel saw an edge; one atomic per warp reserves
+// the slots and every lane with an edge writes at its ballot rank.
+// event = (shifted channel << 40) | (1-based row << 1) | (1 = trailing edge)
+__global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, long long nrows, int M,
+                                                const Thr* __restrict__ thr, int chunk_rows,
+                                                unsigned long long* __restrict__ events,
+                                                unsigned long long cap, unsigned long long* __restrict__ count) {
+  const int lanes_ch = M < 32 ? M : 32;                   // channels per warp
+  const int streams = 32 / lanes_ch;                      // independent row chunks inside one warp (M < 32)
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int ch_groups = (M + 31) / 32;
+  const long long nchunks = (nrows + chunk_rows - 1) / chunk_rows;
+  const long long total_warps = nchunks / streams + (nchunks % streams ? 1 : 0);
+  const long long wchunk = warp_id / ch_groups;
+  if (wchunk >= total_warps) return;                      // warp-uniform
+  const int ch = (int)(warp_id % ch_groups) * 32 + (lane % lanes_ch);
+  const long long chunk = wchunk * streams + lane / lanes_ch;
+  const bool live = chunk < nchunks;
+  const long long r0 = chunk * (long long)chunk_rows;
+  long long r1 = r0 + chunk_rows;
+  if (r1 > nrows) r1 = nrows;
+  const Thr t = thr[ch];
+  const bool exact = t.ge == t.le;                        // threshold is itself a float: equality can occur
+  const unsigned long long chs = (unsigned long long)((ch + M / 2) % M);   // fftshift column (:60), even M
+  // state on entry = state after row r0-1 (0-based): mag > thr, except that exact equality toggles (:88,:94)
+  bool active = false;
+  if (live && r0 > 0) {
+    long long j = r0 - 1;
+    bool flips = false;
+    float m = mag_of(y[j * M + ch]);
+    while (exact && m == t.ge) {
+      flips = !flips;
+      if (--j < 0) break;
+      m = mag_of(y[j * M + ch]);
+    }
+    active = (j < 0 ? false : m > t.le) != flips;
+  }
+  for (int i = 0; i < chunk_rows; i++) {                  // lock-step over the chunk
+    const long long r = r0 + i;
+    bool ev = false;
+    if (live && r < r1) {
+      const float m = mag_of(y[r * M + ch]);
+      if (!active) { if (m >= t.ge) { active = true; ev = true; } }     // leading edge (:88)
+      else if (m <= t.le) { active = false; ev = true; }                // trailing edge (:94)
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, ev);
+    if (ball) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(ball));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (ev) {
+        const unsigned long long slot = base + __popc(ball & ((1u << lane) - 1));
+        if (slot < cap) events[slot] = (chs << 40) | ((unsigned long long)(r + 1) << 1) | (active ? 0ull : 1ull);
+      }
+    }
+  }
+}
+
+// ---- per-pulse statistics ----------------------------------------------------------------------------
+struct PulseIn { unsigned long long toa, end; uint32_t k, kph; };   // rows 1-based, natural channels
+struct PulseOut { float amp_lo, amp_hi, pd_lo, pd_hi; uint32_t sat, pad; };
+
+__device__ __forceinline__ uint32_t fkey(float f) {      // order-preserving map float -> uint32
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+  return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+__device__ __forceinline__ double phase_deg(float2 v) {  // rad2deg(angle(iq)) (:68)
+  return atan2((double)v.y, (double)v.x) * (180.0 / 3.14159265358979323846264338327950288);
+}
+__device__ __forceinline__ float wrapped_diff(float2 a, float2 b) {   // :114-116
+  double d = phase_deg(b) - phase_deg(a);
+  if (d < -180.0) d += 360.0;
+  if (d > 180.0) d -= 360.0;
+  return (float)d;
+}
+
+// Exact k-th smallest (two ranks at once) of n keys produced by key(i), 4 passes of 8 bits.
+template <typename KeyF>
+__device__ void block_select2(KeyF key, unsigned long long n, unsigned long long rank_lo, unsigned long long rank_hi,
+                              uint32_t* h0, uint32_t* h1, uint32_t* out /*[2]*/, unsigned long long* sh_rank) {
+  uint32_t pre[2] = {0u, 0u};
+  unsigned long long rk[2] = {rank_lo, rank_hi};
+  for (int pass = 0; pass < 4; pass++) {
+    const int shift = 24 - 8 * pass;
+    const uint32_t pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { h0[i] = 0; h1[i] = 0; }
+    __syncthreads();
+    const bool split = pre[0] != pre[1];
+    for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t k = key(i);
+      if ((k & pmask) == pre[0]) atomicAdd(&h0[(k >> shift) & 0xFF], 1u);
+      if (split && (k & pmask) == pre[1]) atomicAdd(&h1[(k >> shift) & 0xFF], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      const uint32_t* hh = (threadIdx.x == 1 && split) ? h1 : h0;
+      unsigned long long acc = 0, want = rk[threadIdx.x];
+      int b = 0;
+      for (; b < 255; b++) { if (acc + hh[b] > want) break; acc += hh[b]; }
+      out[threadIdx.x] = (uint32_t)b;
+      sh_rank[threadIdx.x] = want - acc;
+    }
+    __syncthreads();
+    for (int s = 0; s < 2; s++) { pre[s] |= out[s] << shift; rk[s] = sh_rank[s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = pre[0]; out[1] = pre[1]; }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) k_pulse_stats(const float2* __restrict__ y, int M, double sat_level,
+                                                     const PulseIn* __restrict__ in, PulseOut* __restrict__ outp) {
+  __shared__ uint32_t h0[256], h1[256], res[2];
+  __shared__ unsigned long long sh_rank[2];
+  __shared__ int sh_sat;
+  const PulseIn p = in[blockIdx.x];
+  const unsigned long long a = p.toa - 1, b = p.end - 1;   // 0-based inclusive rows
+  if (threadIdx.x == 0) sh_sat = 0;
+  __syncthreads();
+  // saturation: rows strictly between the edges (:129-132 runs only while the pulse stays active)
+  int sat = 0;
+  for (unsigned long long r = a + 1 + threadIdx.x; r < b; r += blockDim.x) {
+    const float2 v = y[r * M + p.k];
+    if ((double)fabsf(v.x) >= sat_level || (double)fabsf(v.y) >= sat_level) sat = 1;   // :130
+  }
+  if (sat) atomicOr(&sh_sat, 1);
+  PulseOut o;
+  // amplitude: median(mag(toa:jj,bin)), both edges included (:101)
+  const unsigned long long n1 = b - a + 1;
+  block_select2([&](unsigned long long i) { return fkey(mag_of(y[(a + i) * M + p.k])); }, n1, (n1 - 1) / 2, n1 / 2,
+                h0, h1, res, sh_rank);
+  o.amp_lo = fkey_inv(res[0]); o.amp_hi = fkey_inv(res[1]);
+  __syncthreads();
+  // frequency: median of the wrapped first difference of the phase in degrees (:114-117)
+  const unsigned long long n2 = b - a;
+  block_select2([&](unsigned long long i) {
+                  return fkey(wrapped_diff(y[(a + i) * M + p.kph], y[(a + i + 1) * M + p.kph]));
+                }, n2, (n2 - 1) / 2, n2 / 2, h0, h1, res, sh_rank);
+  o.pd_lo = fkey_inv(res[0]); o.pd_hi = fkey_inv(res[1]);
+  o.sat = (uint32_t)sh_sat; o.pad = 0;
+  if (threadIdx.x == 0) outp[blockIdx.x] = o;
+}
+
+// ---- host driver ---------------------------------------------------------------------------------------
+template <typename T> struct DevBuf {
+  T* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+};
+
+int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t nrows) {
+  const int M = (int)h->M;
+  cudaStream_t st = h->stream;
+  h->pdws.clear();
+  h->noise_floor.assign(M, NAN);
+  if (nrows == 0) return CHZ_OK;
+
+  // 1. exact per-channel median of |y| (:73)
+  DevBuf<uint32_t> d_hist; DevBuf<SelState> d_sel;
+  CHZ_CUDA(d_hist.alloc((size_t)M * 2 * kBins));
+  CHZ_CUDA(d_sel.alloc(M));
+  CHZ_CUDA(cudaMemsetAsync(d_hist.p, 0, (size_t)M * 2 * kBins * sizeof(uint32_t), st));
+  const uint32_t rank_lo = (uint32_t)((nrows - 1) / 2), rank_hi = (uint32_t)(nrows / 2);
+  long long ychunks = (h->sm_count * 4 + M / 4 - 1) / (M / 4);
+  const long long max_chunks = (long long)((nrows + 255) / 256);
+  if (ychunks > max_chunks) ychunks = max_chunks;
+  if (ychunks < 1) ychunks = 1;
+  if (ychunks > 65535) ychunks = 65535;
+  for (int pass = 0; pass < 3; pass++) {
+    k_hist<<<dim3(M / 4, (unsigned)ychunks), 256, 0, st>>>(y, (long long)nrows, M, pass, d_sel.p, d_hist.p);
+    k_select<<<M, 256, 0, st>>>(d_hist.p, d_sel.p, pass, rank_lo, rank_hi);
+    h->launches += 2;
+  }
+  CHZ_CUDA(cudaGetLastError());
+  std::vector<SelState> sel(M);
+  CHZ_CUDA(cudaMemcpyAsync(sel.data(), d_sel.p, sizeof(SelState) * M, cudaMemcpyDeviceToHost, st));
+  CHZ_CUDA(cudaStreamSynchronize(st));
+
+  // 2. thresholds (:74-75), double on the host, bracketed by floats for the fp32 comparisons
+  const double scale = std::pow(10.0, prm->snr_threshold_db / 10.0);
+  std::vector<Thr> thr(M);
+  for (int k = 0; k < M; k++) {
+    float lo, hi;
+    memcpy(&lo, &sel[k].prefix[0], 4);
+    memcpy(&hi, &sel[k].prefix[1], 4);
+    const double nf = 0.5 * ((double)lo + (double)hi);     // MATLAB median: mean of the two middle values
+    h->noise_floor[k] = nf;
+    const double t = nf * scale;
+    float f = (float)t;                                    // round to nearest
+    float ge = f, le = f;
+    if ((double)f < t) ge = std::nextafterf(f, INFINITY);
+    else if ((double)f > t) le = std::nextafterf(f, -INFINITY);
+    thr[k].ge = ge; thr[k].le = le;
+  }
+  DevBuf<Thr> d_thr;
+  CHZ_CUDA(d_thr.alloc(M));
+  CHZ_CUDA(cudaMemcpyAsync(d_thr.p, thr.data(), sizeof(Thr) * M, cudaMemcpyHostToDevice, st));
+
+  // 3. edge events (:79-96)
+  const int chunk_rows = 64;
+  const long long nchunks = ((long long)nrows + chunk_rows - 1) / chunk_rows;
+  const int lanes_ch = M < 32 ? M : 32, streams = 32 / lanes_ch, ch_groups = (M + 31) / 32;
+  const long long warps = ((nchunks + streams - 1) / streams) * ch_groups;
+  const long long blocks = (warps + 7) / 8;
+  unsigned long long cap = 1ull << 20, nev = 0;
+  DevBuf<unsigned long long> d_cnt;
+  CHZ_CUDA(d_cnt.alloc(1));
+  std::vector<unsigned long long> ev;
+  for (;;) {
+    DevBuf<unsigned long long> d_ev;
+    CHZ_CUDA(d_ev.alloc(cap));
+    CHZ_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), st));
+    k_detect<<<(unsigned)blocks, 256, 0, st>>>(y, (long long)nrows, M, d_thr.p, chunk_rows, d_ev.p, cap, d_cnt.p);
+    h->launches++;
+    CHZ_CUDA(cudaGetLastError());
+    CHZ_CUDA(cudaMemcpyAsync(&nev, d_cnt.p, sizeof nev, cudaMemcpyDeviceToHost, st));
+    CHZ_CUDA(cudaStreamSynchronize(st));
+    if (nev <= cap) {
+      ev.resize(nev);
+      if (nev) CHZ_CUDA(cudaMemcpy(ev.data(), d_ev.p, nev * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      break;
+    }
+    cap = nev;   // rerun with room for everything
+  }
+
+  // 4. pair edges per channel in time order; a pulse still open at the end is dropped (:135)
+  std::sort(ev.begin(), ev.end());
+  std::vector<PulseIn> pulses;
+  const uint32_t kbug = (uint32_t)((0 + (M + 1) / 2) % M);   // natural channel of shifted column 1 (:114)
+  for (size_t i = 0; i + 1 < ev.size(); i++) {
+    const unsigned long long e0 = ev[i], e1 = ev[i + 1];
+    if ((e0 & 1ull) == 0 && (e1 & 1ull) == 1 && (e0 >> 40) == (e1 >> 40)) {
+      PulseIn p;
+      p.toa = (e0 & ((1ull << 40) - 1)) >> 1;
+      p.end = (e1 & ((1ull << 40) - 1)) >> 1;
+      const uint32_t c = (uint32_t)(e0 >> 40);
+      p.k = (c + (uint32_t)(M + 1) / 2) % (uint32_t)M;
+      p.kph = prm->reproduce_phase_bug ? kbug : p.k;
+      pulses.push_back(p);
+      i++;
+    }
+  }
+  if (pulses.empty()) return CHZ_OK;
+
+  // 5. per-pulse medians and saturation (:97-122)
+  DevBuf<PulseIn> d_pin; DevBuf<PulseOut> d_pout;
+  CHZ_CUDA(d_pin.alloc(pulses.size()));
+  CHZ_CUDA(d_pout.alloc(pulses.size()));
+  CHZ_CUDA(cudaMemcpyAsync(d_pin.p, pulses.data(), pulses.size() * sizeof(PulseIn), cudaMemcpyHostToDevice, st));
+  k_pulse_stats<<<(unsigned)pulses.size(), 128, 0, st>>>(y, M, prm->sat_level, d_pin.p, d_pout.p);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  std::vector<PulseOut> pout(pulses.size());
+  CHZ_CUDA(cudaMemcpyAsync(pout.data(), d_pout.p, pulses.size() * sizeof(PulseOut), cudaMemcpyDeviceToHost, st));
+  CHZ_CUDA(cudaStreamSynchronize(st));
+
+  // 6. records (:97-128), already in the reference's order: shifted channel ascending, then time
+  const double fs_dec = prm->fs_sps / (double)h->D;        // :62
+  h->pdws.resize(pulses.size());
+  for (size_t i = 0; i < pulses.size(); i++) {
+    const PulseIn& p = pulses[i];
+    const PulseOut& o = pout[i];
+    chz_pdw_t r;
+    memset(&r, 0, sizeof r);
+    const uint32_t c = (p.k + (uint32_t)(M / 2)) % (uint32_t)M;
+    const double bin_freq = ((double)c - (double)(M / 2)) * prm->fs_sps / (double)M;   // :42 on shifted columns
+    const double nf = h->noise_floor[p.k];
+    const double med_pd = 0.5 * ((double)o.pd_lo + (double)o.pd_hi);
+    r.toa_s = ((double)p.toa / fs_dec) + prm->t0;                                       // :98
+    r.amp = 0.5 * ((double)o.amp_lo + (double)o.amp_hi);                                // :101
+    r.snr_db = 10.0 * std::log10(r.amp / nf);                                           // :105
+    r.pw_s = (double)(p.end - p.toa) / fs_dec;                                          // :110
+    r.freq_hz = (prm->fc_hz + bin_freq) + (fs_dec / (360.0 / med_pd));                  // :80, :122
+    r.noise_floor = nf;
+    r.channel = c; r.channel_natural = p.k;
+    r.toa_row = p.toa; r.end_row = p.end; r.saturated = o.sat;
+    h->pdws[i] = r;
+  }
+  return CHZ_OK;
+}
+
+}  // namespace chzi

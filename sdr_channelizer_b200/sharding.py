@@ -1,0 +1,58 @@
+"""Time sharding of one recording across GPUs (BASELINE.json configs[3]).
+
+Output row m depends only on samples x[m*D - (L-1) .. m*D], so the recording splits into contiguous
+row ranges; shard g reads its own samples plus a halo of L-1 = taps-1 preceding samples (zeros for
+shard 0).  Shards are independent: no collective on the channelizer path, rows are stitched in
+time order on the host.  Feeding the halo through the same channelizer first (and discarding the
+rows it produces) makes the shard's FIR state identical to the single-GPU run, so results are
+bit-identical by construction.
+"""
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class TimeShard:
+    rank: int
+    row_begin: int        # first output row owned (global index)
+    row_end: int          # one past the last owned row
+    sample_begin: int     # first sample to feed (includes the halo, frame aligned)
+    sample_end: int       # one past the last sample to feed
+    discard_rows: int     # rows produced by the halo that belong to the previous shard
+
+    @property
+    def rows(self):
+        return self.row_end - self.row_begin
+
+    @property
+    def samples(self):
+        return self.sample_end - self.sample_begin
+
+
+def plan_time_shards(num_samples, M, ntaps, oversample, world_size):
+    """Split floor(num_samples / D) rows into world_size contiguous ranges.
+
+    Each shard starts feeding at a frame boundary at least (taps-1) samples before its first owned
+    row's newest sample, rounded down to a multiple of M so the circular branch rotation (m*D mod M)
+    restarts in phase.  Rows the halo itself produces are discarded (their FIR history is incomplete).
+    """
+    D = M // oversample
+    total_rows = num_samples // D
+    shards = []
+    base, extra = divmod(total_rows, world_size)
+    row = 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        rb, re = row, row + n
+        row = re
+        # newest sample of row rb is rb*D; oldest it touches is rb*D - (ntaps-1)
+        start = max(0, rb * D - (ntaps - 1))
+        start = (start // M) * M                      # frame- and rotation-aligned
+        discard = rb - start // D                     # rows start//D .. rb-1 come out of the halo
+        shards.append(TimeShard(r, rb, re, start, re * D, discard))
+    return shards
+
+
+def stitch_rows(parts):
+    """Concatenate per-shard row blocks (already trimmed of their discard rows) in rank order."""
+    import numpy as np
+    return np.concatenate(list(parts), axis=0) if parts else None

@@ -1,0 +1,230 @@
+"""Parity tests proper: the CUDA path through the C ABI against the CPU oracle, on a real B200.
+Tolerances are north_star's: unpack bit-exact; channel outputs rel. RMS <= 1e-5 vs the double oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import sdr_channelizer_b200 as pkg
+from sdr_channelizer_b200 import _lib
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # relative RMS, BASELINE.json north_star
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return torch
+
+
+def _gen(kind, n, M, seed):
+    if kind == "i8":
+        return synth.tones_int8(n, M, seed)
+    if kind == "q11":
+        return synth.tones_int16_q11(n, M, seed)
+    return synth.noise_int16_full(n, seed)
+
+
+# ---- K1 ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bw", [8, 5, 12, 16])
+def test_unpack_bit_exact_all_values(orc, bw):
+    torch = _torch()
+    if bw <= 8:
+        v = np.arange(-128, 128, dtype=np.int8)
+        iq = np.stack([np.tile(v, 3), np.tile(v[::-1], 3)], axis=1)
+    else:
+        v = np.arange(-32768, 32768, dtype=np.int16)
+        iq = np.stack([v, np.roll(v[::-1], 77)], axis=1)
+    d_in = torch.from_numpy(iq).cuda()
+    d_out = torch.empty((iq.shape[0], 2), dtype=torch.float32, device="cuda")
+    pkg.unpack_ptr(d_in.data_ptr(), iq.shape[0], bw, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    ref = orc.unpack(iq, bw)
+    assert np.array_equal(got[:, 0].astype(np.float64), ref.real) and np.array_equal(got[:, 1].astype(np.float64), ref.imag)
+
+
+# ---- K3 against cuFFT ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("M", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+def test_fft_stage_matches_cufft(M):
+    torch = _torch()
+    rows = 37 if M >= 1024 else 333
+    g = torch.Generator(device="cuda").manual_seed(M)
+    u = torch.randn((rows, M), dtype=torch.complex64, device="cuda", generator=g)
+    y = torch.empty_like(u)
+    ch = pkg.Channelizer(M, NumTapsPerBand=8)
+    ch.set_stream(torch.cuda.current_stream().cuda_stream)
+    ch.fft_rows_ptr(u.data_ptr(), y.data_ptr(), rows)
+    torch.cuda.synchronize()
+    ref = torch.fft.ifft(u.to(torch.complex128), dim=1) * M          # cuFFT, e^{+j} exponent, unnormalised
+    err = (torch.linalg.norm(y.to(torch.complex128) - ref) / torch.linalg.norm(ref)).item()
+    assert err < 2e-6, err
+    ch.close()
+
+
+# ---- fused / split channelizer against the oracle --------------------------------------------------------
+CASES = [
+    # M, P, oversample, input kind, samples
+    (8, 8, 1, "i8", 1_000_000),          # configs[0]
+    (8, 12, 2, "i8", 100_003),
+    (16, 12, 1, "q11", 50_000),
+    (32, 16, 2, "q11", 64_000),
+    (64, 16, 1, "q11", 64 * 5000 + 17),  # configs[1] geometry
+    (64, 12, 1, "i8", 64 * 3000),
+    (64, 8, 2, "full", 64 * 3000),
+    (128, 16, 1, "q11", 128 * 1500),
+    (256, 16, 1, "full", 256 * 1100),    # configs[4] geometry
+    (256, 12, 2, "q11", 256 * 600),
+    (512, 16, 1, "q11", 512 * 400),
+    (1024, 16, 2, "full", 1024 * 300),   # configs[2] geometry
+    (4096, 16, 1, "q11", 4096 * 100),    # configs[3] geometry
+    (2048, 12, 2, "i8", 2048 * 64),
+    (64, 4, 1, "q11", 64 * 2000),        # split path (no fused instantiation for P=4)
+    (64, 5, 1, "q11", 64 * 500),         # generic-P fallback
+]
+
+
+@pytest.mark.parametrize("M,P,os_,kind,n", CASES)
+def test_channelizer_matches_oracle(orc, M, P, os_, kind, n):
+    _torch()
+    iq, bw = _gen(kind, n, M, seed=M + P)
+    taps = pkg.design_prototype(M, P)
+    ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=os_)
+    y = ch(iq, bw)
+    ref = orc.channelize_raw(iq, bw, M, taps.astype(np.float64), os_)
+    assert y.shape == ref.shape == (n // (M // os_), M)
+    err = synth.rel_rms(y, ref)
+    assert err <= TOL, err
+    # row 0 depends on x[0] only: exact product of one tap and one sample
+    assert abs(y[0, 0] - ref[0, 0]) <= 1e-6 * abs(ref[0, 0]) + 1e-12
+    ch.close()
+
+
+@pytest.mark.parametrize("M,P,os_", [(64, 16, 1), (64, 16, 2), (256, 12, 1), (8, 8, 1)])
+def test_split_path_equals_fused_path(M, P, os_):
+    _torch()
+    iq, bw = synth.tones_int16_q11(M * 900 + 5, M, seed=3)
+    taps = pkg.design_prototype(M, P)
+    outs = []
+    for path in (1, 2):
+        ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=os_)
+        ch.set_option(_lib.CHZ_OPT_FORCE_PATH, path)
+        outs.append(ch(iq, bw))
+        ch.close()
+    assert synth.rel_rms(outs[0], outs[1]) < 1e-6
+
+
+@pytest.mark.parametrize("M,P,os_", [(64, 16, 1), (32, 12, 2), (1024, 16, 2), (8, 8, 1)])
+def test_streaming_chunks_are_bit_identical_to_one_shot(M, P, os_):
+    """Stateful like the System object (channelizer_example.m:50-56): ragged chunk sizes, including
+    ones shorter than a frame, give exactly the rows of a single call."""
+    _torch()
+    n = M * 700 + 13
+    iq, bw = synth.tones_int16_q11(n, M, seed=9)
+    taps = pkg.design_prototype(M, P)
+    ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=os_)
+    whole = ch(iq, bw).copy()
+    ch.reset()
+    rng = np.random.default_rng(1)
+    parts, pos = [], 0
+    while pos < n:
+        step = int(rng.choice([1, 3, M // 2, M, M + 1, 5 * M + 7, 100 * M]))
+        parts.append(ch(iq[pos:pos + step], bw).copy())
+        pos += step
+    got = np.concatenate(parts, axis=0)
+    assert got.shape == whole.shape and np.array_equal(got.view(np.float32), whole.view(np.float32))
+    ch.close()
+
+
+def test_host_chunked_pipeline_equals_single_chunk():
+    _torch()
+    M = 64
+    iq, bw = synth.tones_int16_q11(M * 5000, M, seed=4)
+    taps = pkg.design_prototype(M, 16)
+    ch = pkg.Channelizer(M, taps=taps)
+    a = ch(iq, bw).copy()
+    ch.reset()
+    ch.set_option(_lib.CHZ_OPT_CHUNK_ROWS, 333)      # many small pipelined chunks
+    ch.set_option(_lib.CHZ_OPT_RETAIN, 0)
+    b = ch(iq, bw).copy()
+    assert np.array_equal(a.view(np.float32), b.view(np.float32))
+    ch.close()
+
+
+def test_impulse_and_tone_known_answers():
+    _torch()
+    M, P = 64, 16
+    taps = pkg.design_prototype(M, P)
+    ch = pkg.Channelizer(M, taps=taps)
+    iq = np.zeros((M * 40, 2), dtype=np.int16); iq[0, 0] = 2047
+    y = ch(iq, 12)
+    for m in range(P):      # impulse -> row m is the constant taps[m*M] * x[0] in every channel
+        assert np.allclose(y[m], taps[m * M] * (2047 / 2048), rtol=1e-6, atol=1e-12)
+    assert np.all(y[P:] == 0)
+    ch.reset()
+    k0 = 11
+    n = np.arange(M * 400)
+    x = 0.5 * np.exp(2j * np.pi * k0 * n / M)
+    iq = np.stack([np.rint(x.real * 32768), np.rint(x.imag * 32768)], axis=1).astype(np.int16)
+    y = ch(iq, 16)
+    assert abs(abs(y[-1, k0]) - 0.5) < 1e-4 and np.max(np.abs(np.delete(y[-1], k0))) < 1e-3
+    ch.close()
+
+
+def test_capacity_and_state_errors():
+    torch = _torch()
+    ch = pkg.Channelizer(64, NumTapsPerBand=16)
+    iq = np.zeros((64 * 10, 2), dtype=np.int16)
+    out = np.empty((3, 64), dtype=np.complex64)
+    n = C.c_uint64(0)
+    rc = pkg.lib().chz_process(ch.handle, iq.ctypes.data_as(C.c_void_p), 640, 12, out.ctypes.data_as(C.c_void_p), 3, C.byref(n))
+    assert rc == _lib.CHZ_ECAPACITY and n.value == 10
+    assert ch(iq, 12).shape == (10, 64)
+    with pytest.raises(pkg.ChannelizerError):      # bit width may not change mid-stream
+        ch(iq, 16)
+    ch.reset()
+    assert ch(iq, 16).shape == (10, 64)
+    assert ch(np.zeros((0, 2), dtype=np.int16), 16).shape == (0, 64)
+    with pytest.raises(pkg.ChannelizerError):
+        ch(iq, 17)
+    ch.close()
+
+
+# ---- size-independent properties at (near) BASELINE size ------------------------------------------------
+def test_large_run_spot_rows_and_linearity(orc):
+    """configs[1] geometry on ~0.6 s of 61.44 MS/s (37.7 M samples, device resident): random rows are
+    checked against the oracle evaluated on just the samples those rows touch, and the transform is
+    linear: chan(a) + chan(b) == chan(a + b) when a + b does not clip."""
+    torch = _torch()
+    M, P, bw = 64, 16, 12
+    n = 64 * 589_000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randint(-900, 900, (n, 2), dtype=torch.int16, device="cuda", generator=g)
+    b = torch.randint(-900, 900, (n, 2), dtype=torch.int16, device="cuda", generator=g)
+    taps = pkg.design_prototype(M, P)
+    ch = pkg.Channelizer(M, taps=taps)
+    ch.set_stream(torch.cuda.current_stream().cuda_stream)
+    rows = n // M
+    outs = []
+    for src in (a, b, a + b):
+        ch.reset()
+        y = torch.empty((rows, M), dtype=torch.complex64, device="cuda")
+        assert ch.process_ptr(src.data_ptr(), n, bw, y.data_ptr(), rows) == rows
+        outs.append(y)
+    torch.cuda.synchronize()
+    lin = (torch.linalg.norm(outs[0] + outs[1] - outs[2]) / torch.linalg.norm(outs[2])).item()
+    assert lin < 1e-6, lin
+    rng = np.random.default_rng(0)
+    L = M * P
+    for m in [0, 1, P - 1, rows - 1] + [int(v) for v in rng.integers(P, rows, 24)]:
+        lo = max(0, m * M - (L - 1))
+        seg = a[lo:m * M + 1].cpu().numpy()                                   # x[mM-L+1 .. mM], clipped at 0
+        seg_full = np.concatenate([np.zeros((L - len(seg), 2), np.int16), seg])
+        # window with x[mM] at index L = P*M: its row P is row m of the full run
+        win = np.concatenate([np.zeros((1, 2), np.int16), seg_full, np.zeros((M - 1, 2), np.int16)])
+        ref = orc.channelize_raw(win, bw, M, taps.astype(np.float64))[P]
+        got = outs[0][m].cpu().numpy()
+        assert synth.rel_rms(got, ref) <= TOL, m
+    ch.close()

@@ -1,0 +1,127 @@
+"""PDW extraction (K4) through the C ABI against the oracle's transcription of
+matlab/create_pdws_channelized.m:60-136.  north_star: record counts bit-exact, TOA/PW within +-1 row."""
+import numpy as np
+import pytest
+
+import sdr_channelizer_b200 as pkg
+from tests import synth
+from tests.test_oracle import _pulse_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _pdws_on_matrix(y, fs, **kw):
+    """Run K4 on a hand-built channel matrix (complex64 on the device)."""
+    torch = _torch()
+    M = y.shape[1]
+    d = torch.from_numpy(np.ascontiguousarray(y.astype(np.complex64))).cuda()
+    ch = pkg.Channelizer(M, NumTapsPerBand=8)
+    ch.set_stream(torch.cuda.current_stream().cuda_stream)
+    recs, nf = ch.pdws_ptr(d.data_ptr(), y.shape[0], fs, **kw)
+    ch.close()
+    return recs, nf
+
+
+def _compare(recs, orecs, fs_dec, tol_rows=1):
+    assert len(recs) == len(orecs), (len(recs), len(orecs))
+    for a, b in zip(recs, orecs):
+        assert (a.channel, a.channel_natural) == (b.channel, b.channel_natural)
+        assert abs(int(a.toa_row) - int(b.toa_row)) <= tol_rows
+        assert abs(int(a.end_row - a.toa_row) - int(b.end_row - b.toa_row)) <= tol_rows
+        assert abs(a.toa_s - b.toa_s) <= tol_rows / fs_dec + 1e-12 and abs(a.pw_s - b.pw_s) <= tol_rows / fs_dec + 1e-12
+        assert a.saturated == b.saturated
+        assert abs(a.amp - b.amp) <= 1e-5 * b.amp and abs(a.snr_db - b.snr_db) <= 1e-3
+        assert abs(a.freq_hz - b.freq_hz) <= 1e-4 * fs_dec, (a.freq_hz, b.freq_hz)
+
+
+def test_known_answer_matrix(orc):
+    M, fs, fc, t0 = 8, 8e6, 1e9, 1000.0
+    y, k1, k2 = _pulse_matrix(M)
+    y = y.astype(np.complex64)               # the oracle sees exactly the fp32 values the GPU gets
+    recs, nf = _pdws_on_matrix(y, fs, fc=fc, sampleStartTime=t0)
+    orecs, onf = orc.pdws(y.astype(np.complex128), M, fc_hz=fc, fs_sps=fs, t0=t0)
+    assert np.allclose(nf, onf, rtol=2e-7)
+    _compare(recs, orecs, fs / M, tol_rows=0)
+    assert [(r.toa_row, r.end_row) for r in recs] == [(201, 232), (101, 152)]
+    assert [r.saturated for r in recs] == [1, 0]
+
+
+def test_fsm_equality_toggle_and_open_pulse(orc):
+    """SNR_THRESHOLD = 0 dB and a median of 2^-6 make the threshold exactly representable, so samples
+    EQUAL to it occur: >= opens and <= closes on the same value (:88,:94), i.e. equality toggles the
+    state sample by sample.  Long runs of equal samples cross the detector's 64-row chunks."""
+    M, rows = 8, 301
+    y = np.full((rows, M), 2.0 ** -6, dtype=np.complex64)
+    y[100:111, 3] = 0                       # below: forces inactive
+    y[150:156, 3] = 1.5 * 2.0 ** -6         # above: forces active
+    y[200:203, 5] = 3.0 * 2.0 ** -6
+    y[rows - 1, 6] = 1.0                    # pulse still open at the end of the file: dropped (:135)
+    recs, nf = _pdws_on_matrix(y, 8e6, SNR_THRESHOLD=0.0)
+    orecs, onf = orc.pdws(y.astype(np.complex128), M, snr_threshold_db=0.0, fs_sps=8e6)
+    assert np.all(nf == 2.0 ** -6) and np.all(onf == 2.0 ** -6)
+    assert len(orecs) > 4 * (rows // 2 - 10)
+    _compare(recs, orecs, 1e6, tol_rows=0)
+
+
+def test_saturation_not_checked_on_edges(orc):
+    M = 8
+    y, k1, k2 = _pulse_matrix(M)
+    y[210, k2] = 0.5
+    y[200, k2] = 1.0
+    y = y.astype(np.complex64)
+    recs, _ = _pdws_on_matrix(y, 8e6)
+    orecs, _ = orc.pdws(y.astype(np.complex128), M, fs_sps=8e6)
+    _compare(recs, orecs, 1e6, tol_rows=0)
+    assert [r.saturated for r in recs] == [0, 0]
+
+
+def test_phase_bug_flag(orc):
+    M = 8
+    y, k1, k2 = _pulse_matrix(M)
+    y[:, M // 2] = 0.01 * np.exp(1j * 0.5 * np.arange(y.shape[0]))
+    y = y.astype(np.complex64)
+    for flag in (False, True):
+        recs, _ = _pdws_on_matrix(y, 8e6, reproduce_phase_bug=flag)
+        orecs, _ = orc.pdws(y.astype(np.complex128), M, fs_sps=8e6, reproduce_phase_bug=flag)
+        _compare(recs, orecs, 1e6, tol_rows=0)
+
+
+def test_no_pulses_and_empty():
+    rng = np.random.default_rng(0)
+    y = (rng.standard_normal((1000, 16)) + 1j * rng.standard_normal((1000, 16))).astype(np.complex64)
+    recs, nf = _pdws_on_matrix(y, 16e6)
+    assert recs == [] and np.allclose(nf, np.median(np.abs(y), axis=0), rtol=1e-6)
+
+
+@pytest.mark.parametrize("M,P,seed", [(256, 16, 100), (256, 16, 101), (64, 12, 102), (1024, 16, 103), (8, 8, 104)])
+def test_end_to_end_pulsed_recording(orc, M, P, seed, tmp_path):
+    """configs[4]: generate_channelized_training_iq-style file -> channelizer -> PDWs, via the file
+    reader and create_pdws_channelized(), against the oracle run on the same bytes."""
+    _torch()
+    n = M * 9000
+    iq, bw, fs = synth.pulsed_int16(n, M=M, seed=seed)
+    path = str(tmp_path / "pulsed.iq")
+    pkg.write_iq(path, iq, fs=fs, fc=2.4e9, bitWidth=bw, sampleStartTime=1.7e9, fileFormat=1 if M <= 64 else 3)
+    taps = pkg.design_prototype(M, P)
+    rec = pkg.read_iq(path)
+    ch = pkg.Channelizer(M, taps=taps)
+    y = ch(rec.iq, rec.bitWidth)
+    recs, nf = ch.pdws(rec.fs, rec.fc, rec.sampleStartTime)
+    ch.close()
+    oy = orc.channelize_raw(rec.iq, rec.bitWidth, M, taps.astype(np.float64))
+    assert synth.rel_rms(y, oy) <= 1e-5
+    orecs, onf = orc.pdws(oy, M, fc_hz=rec.fc, fs_sps=rec.fs, t0=rec.sampleStartTime)
+    assert len(orecs) >= 3, "generator should produce several pulses"
+    assert np.allclose(nf, onf, rtol=1e-4)
+    _compare(recs, orecs, rec.fs / M, tol_rows=1)
+    # the script-level entry point gives the same table
+    pdw = pkg.create_pdws_channelized([path], M=M, taps=taps)
+    assert len(pdw["toa"]) == len(orecs)
+    assert np.allclose(pdw["toa"], [r.toa_s for r in orecs], atol=1.0 / (rec.fs / M) + 1e-9)
+    assert np.array_equal(pdw["sat"], [bool(r.saturated) for r in orecs])
