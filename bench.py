@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json configs[1]):
+
+    64-channel critically sampled channelizer, 1024-tap prototype, on a 12-bit bladeRF-format
+    recording at 61.44 MS/s, 10 s long (614.4 M complex int16 samples = 2.46 GB in, 4.92 GB out).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one pass of unpack -> polyphase FIR -> FFT over one recording.  N GPUs: the recording is N
+times longer and is sharded along time, rank r taking 10 s plus a (taps-1)-sample halo — no
+collective on the data path (weak scaling).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+M, TAPS_PER_BAND, OVERSAMPLE, BIT_WIDTH = 64, 16, 1, 12
+FS = 61_440_000
+SECONDS = 10
+N_SAMPLES = FS * SECONDS                      # per GPU
+BYTES_PER_SAMPLE_ALGO = 4 + 8 * OVERSAMPLE    # int16 pair in, fp32 complex out
+METRIC = "input complex MS/s channelized"
+WORKLOAD = ("configs[1]: 64-channel critically sampled channelizer, 1024-tap prototype, 12-bit bladeRF-format "
+            "recording at 61.44 MS/s, 10 s per GPU")
+
+
+def _peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic_from_profiles():
+    try:
+        with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch_full_workload")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [l for (t, l) in self.lines if t0 <= t <= t1 + 0.2] or [l for (_, l) in self.lines]
+        for line in rows:
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except Exception:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_input(torch, n, seed, device):
+    """configs[1] content: 8 tones + AWGN (sigma 0.05 FS) in 12-bit Q11, clipped to [-2048, 2047]."""
+    out = torch.empty((n, 2), dtype=torch.int16, device=device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    freqs = [(-27.3 + 7.1 * i) / M for i in range(8)]
+    chunk = 1 << 24
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        t = torch.arange(s, e, device=device, dtype=torch.float64)
+        re = torch.randn(e - s, device=device, generator=g) * 0.05
+        im = torch.randn(e - s, device=device, generator=g) * 0.05
+        for f in freqs:
+            ph = (2.0 * torch.pi) * torch.frac(t * f)
+            re += 0.08 * torch.cos(ph).float()
+            im += 0.08 * torch.sin(ph).float()
+        out[s:e, 0] = torch.clamp(torch.round(re * 2048.0), -2048, 2047).to(torch.int16)
+        out[s:e, 1] = torch.clamp(torch.round(im * 2048.0), -2048, 2047).to(torch.int16)
+    return out
+
+
+def cpu_baseline(taps, target_seconds=12.0):
+    """The double-precision OpenMP oracle (kind 'port': MATLAB's dsp.Channelizer cannot run here) timed on
+    this box's host cores on a bounded prefix of the same workload."""
+    import numpy as np
+    from oracle import pyoracle as orc
+    from tests import synth
+    h = taps.astype(np.float64)
+    probe_n = M * 32768
+    iq, bw = synth.tones_int16_q11(probe_n, M, seed=2)
+    orc.channelize_raw(iq, bw, M, h, OVERSAMPLE)            # warm-up (threads, page faults)
+    t0 = time.perf_counter(); orc.channelize_raw(iq, bw, M, h, OVERSAMPLE); dt = time.perf_counter() - t0
+    rate = probe_n / dt
+    n = int(min(FS, max(probe_n, rate * target_seconds / 3))) // M * M      # at most a 1 s prefix
+    reps = max(1, int(np.ceil(n / probe_n)))
+    big = np.tile(iq, (reps, 1))[:n]
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter(); orc.channelize_raw(big, bw, M, h, OVERSAMPLE); dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": n / best / 1e6, "unit": "MS/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": f"first {n} samples ({n / FS:.3f} s) of the recording, best of 3, oracle/chz_oracle.cpp "
+                      f"(double precision, OpenMP)"}, n, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  Its arithmetic is MATLAB's
+    closed-source dsp.Channelizer (not runnable here), so this arm times the oracle port on the host
+    cores, each step a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    from oracle import pyoracle as orc
+    from tests import synth
+    taps = orc.design_prototype(M, TAPS_PER_BAND)
+    n = M * 32768 * 8                                          # 16.8 M samples per step (0.27 s of signal)
+    iq, bw = synth.tones_int16_q11(M * 32768, M, seed=2)
+    big = np.tile(iq, (8, 1))
+    for _ in range(max(1, min(args.warmup, 2))):
+        orc.channelize_raw(big, bw, M, taps, OVERSAMPLE)
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.channelize_raw(big, bw, M, taps, OVERSAMPLE)
+    dt = (time.perf_counter() - t0) / steps
+    val = n / dt / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MS/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_per_step": f"{n} samples of that recording per step (bounded CPU sample)",
+                       "note": "reference arithmetic is MATLAB dsp.Channelizer (closed source, no MATLAB/Octave here); "
+                               "timed: oracle/chz_oracle.cpp port, all host threads"},
+            "cpu_baseline": {"value": val, "unit": "MS/s", "cores": orc.num_threads(), "kind": "port",
+                             "sample": f"{n} samples per step"},
+            "e2e": {"value": val, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--seconds", type=float, default=float(SECONDS), help="recording length per GPU (default: the config's 10 s)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import sdr_channelizer_b200 as pkg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: sdr_channelizer_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(3, args.warmup)
+    n_own = int(FS * args.seconds) // M * M
+    ntaps = M * TAPS_PER_BAND
+
+    # time shard of a world*seconds recording: own samples plus the (taps-1)-sample halo, frame aligned
+    shard = pkg.plan_time_shards(n_own * world, M, ntaps, OVERSAMPLE, world)[rank]
+    halo = n_own * rank - shard.sample_begin
+    x = make_input(torch, shard.samples, 2 + rank, dev)           # [halo + own, 2] int16, device resident
+    rows_total = shard.samples // (M // OVERSAMPLE)
+    y = torch.empty((rows_total, M), dtype=torch.complex64, device=dev)
+    taps = pkg.design_prototype(M, TAPS_PER_BAND)
+    ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=OVERSAMPLE)
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)        # the kernels AND the timing events live on this stream
+    torch.cuda.set_stream(stream)
+    ch.set_stream(stream.cuda_stream)
+
+    def step():
+        ch.reset()
+        return ch.process_ptr(x.data_ptr(), shard.samples, BIT_WIDTH, y.data_ptr(), rows_total)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    launches0 = ch.kernel_launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    t_wall0 = time.time()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        rows = step()
+        ev[i + 1].record(stream)
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    assert rows == rows_total
+    per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    launches = ch.kernel_launches - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    value = (n_own * world) / (ms_per_step * 1e-3) / 1e6      # owned samples of all ranks / max time
+
+    # roofline of the dominant kernel (fused unpack+FIR+FFT: one launch per step), rank-0 numbers
+    peak, peak_src = _peak_hbm()
+    kern_ms = statistics.mean(per_step_ms)
+    achieved = shard.samples * BYTES_PER_SAMPLE_ALGO / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": _traffic_from_profiles(), "kernel": "k_chan_fused<64,16,int16>",
+                "algorithmic_bytes_per_launch": shard.samples * BYTES_PER_SAMPLE_ALGO,
+                "ms_per_launch": kern_ms, "ms_per_launch_min": min(per_step_ms), "peak_source": peak_src}
+
+    # end to end through the C ABI with HOST buffers: pinned input -> H2D -> kernels -> D2H -> pinned output
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.empty((shard.samples, 2), dtype=torch.int16, pin_memory=True)
+        h_in.copy_(x)
+        h_out = torch.empty((rows_total, M), dtype=torch.complex64, pin_memory=True)
+        ch.set_option(pkg.CHZ_OPT_RETAIN, 0)
+        e_steps = max(2, min(5, args.steps))
+
+        def e2e_step():
+            ch.reset()
+            return ch.process_ptr(h_in.data_ptr(), shard.samples, BIT_WIDTH, h_out.data_ptr(), rows_total, device=False)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()                                          # synchronous: returns when the output is on the host
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / e_steps], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": (n_own * world) / float(dt.item()) / 1e6, "unit": "MS/s",
+               "h2d_bytes_per_step": int(h_in.numel() * 2), "d2h_bytes_per_step": int(h_out.numel() * 8),
+               "ms_per_step": float(dt.item()) * 1e3, "steps": e_steps,
+               "how": "chz_process() on pinned host buffers, chunked H2D/kernel/D2H pipeline inside the call"}
+        # spot check: the host-path output equals the device-path output
+        chk = torch.equal(h_out[-4:].to(dev).view(torch.float32), y[-4:].view(torch.float32))
+        e2e["matches_device_path"] = bool(chk)
+        del h_in, h_out
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _, _ = cpu_baseline(taps)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "channels": M, "taps": ntaps, "oversample": OVERSAMPLE,
+                           "bit_width": BIT_WIDTH, "samples_per_gpu": n_own, "halo_samples": int(halo),
+                           "parallelism": f"time-sharded x{world}, no collective",
+                           "l2": "inputs (2.46 GB) and outputs (4.92 GB) per step exceed the 126 MB L2; no flush needed"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ch.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

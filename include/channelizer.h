@@ -99,7 +99,9 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
 void chz_destroy(chz_t* h);
 int chz_reset(chz_t* h);
 
-/* Launch all work of this handle on the given cudaStream_t (NULL = the handle's own stream). */
+/* Launch all work of this handle on the given cudaStream_t.  Until this is called the handle uses
+ * its own non-blocking stream.  NULL means CUDA's default stream (as for any cudaStream_t);
+ * (void*)-1 selects the handle's own stream again. */
 int chz_set_stream(chz_t* h, void* cuda_stream);
 
 /* Options (chz_set_option) */

@@ -162,7 +162,10 @@ class Channelizer:
         return np.fft.fftshift(nat)
 
     def set_stream(self, cuda_stream_ptr):
-        check(lib().chz_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "chz_set_stream")
+        """cudaStream_t as an integer (e.g. torch.cuda.current_stream().cuda_stream; 0 = default stream);
+        None selects the handle's own non-blocking stream."""
+        ptr = C.c_void_p(-1) if cuda_stream_ptr is None else C.c_void_p(int(cuda_stream_ptr))
+        check(lib().chz_set_stream(self._h, ptr), "chz_set_stream")
 
     def set_option(self, opt, value):
         check(lib().chz_set_option(self._h, opt, int(value)), "chz_set_option")

@@ -375,7 +375,9 @@ int chz_reset(chz_t* h) {
 
 int chz_set_stream(chz_t* h, void* cuda_stream) {
   if (!h) return CHZ_EINVAL;
-  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  // NULL is CUDA's default stream, exactly as for any cudaStream_t argument; (void*)-1 goes back to the
+  // handle's own non-blocking stream.
+  h->stream = cuda_stream == (void*)(intptr_t)-1 ? h->own_stream : (cudaStream_t)cuda_stream;
   return CHZ_OK;
 }
 
