@@ -109,9 +109,18 @@ template <> struct Plan<1024> { static constexpr int np = 3; static constexpr in
 template <> struct Plan<2048> { static constexpr int np = 3; static constexpr int r0 = 16, r1 = 16, r2 = 8; };
 template <> struct Plan<4096> { static constexpr int np = 3; static constexpr int r0 = 16, r1 = 16, r2 = 16; };
 
-// Padded element index inside one row of the shared tile (8-byte elements): one pad element per 16.
-__device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
-template <int M> struct RowStride { static constexpr int value = M + M / 16 + (M < 16 ? 1 : 0); };
+// Padded element index inside one row of the shared tile (8-byte elements, 16 per 128-byte bank
+// row).  One pad element per 2^PadShift elements, and a row stride chosen so that the half-warps of
+// every pass (a few butterflies of several consecutive rows) hit 16 distinct 8-byte bank pairs both
+// when they read with stride M/R and when they write the Stockham-transposed result:
+//   M = 32 (radix 8,4):  4 butterflies per row  -> pad every 8, rows 4 bank pairs apart (stride 36)
+//   M = 64 (radix 8,8):  8 butterflies per row  -> pad every 8, rows 8 apart           (stride 72)
+//   M >= 128 (first radix 16): pad every 16, rows 8 apart for M = 128, irrelevant above
+template <int M> struct PadShift { static constexpr int value = (M == 32 || M == 64) ? 3 : 4; };
+template <int M> __device__ __forceinline__ int padi(int i) { return i + (i >> PadShift<M>::value); }
+template <int M> struct RowStride {
+  static constexpr int value = M == 32 ? 36 : (M == 64 ? 72 : M + M / 16 + (M < 16 ? 1 : 0));
+};
 
 // One Stockham pass of radix R over `rows` rows of length M held in shared memory.
 //   src/dst : [rows][RowStride<M>] float2 (padded with padi)
@@ -130,7 +139,7 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, fl
     const float2* s = src + row * S;
     float2 v[R];
     #pragma unroll
-    for (int q = 0; q < R; q++) v[q] = s[padi(j + q * BPR)];
+    for (int q = 0; q < R; q++) v[q] = s[padi<M>(j + q * BPR)];
     const int k = j & (Ns - 1);   // j mod Ns (Ns is a power of two)
     if (Ns > 1) {
       const int tstep = (M / R) / Ns;   // table stride: W_{Ns R}^{q k} = W_M^{q k M/(Ns R)}
@@ -148,7 +157,7 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, fl
     } else {
       float2* d = dst + row * S;
       #pragma unroll
-      for (int q = 0; q < R; q++) d[padi(j0 + q * Ns)] = v[q];
+      for (int q = 0; q < R; q++) d[padi<M>(j0 + q * Ns)] = v[q];
     }
   }
 }

@@ -75,35 +75,56 @@ __device__ __forceinline__ Span make_span(const ChanParams& p, long long sp) {
 template <int P, bool IN16, typename Emit>
 __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, int p, Emit emit) {
   typedef typename RawT<IN16>::type raw_t;
-  float2 hh[P], w[P];
+  float h[P];
+  float2 w[P];
   #pragma unroll
-  for (int q = 0; q < P; q++) { const float h = __ldg(prm.taps + q * prm.M + p); hh[q] = make_float2(h, h); }
+  for (int q = 0; q < P; q++) h[q] = __ldg(prm.taps + q * prm.M + p);
   const long long base = sp.m0 * prm.D - p;   // newest sample of span row 0 for this branch
   const long long Ml = prm.M;
   const long long in_end = prm.in_base + prm.n_in;
   const raw_t* __restrict__ inp = (const raw_t*)prm.in - prm.in_base;   // inp[idx] for idx in [in_base, in_end)
-  // warm-up: rows -(P-1)..-1 go to slots 1..P-1 (row -k -> slot P-k)
-  w[0] = make_float2(0.f, 0.f);
-  #pragma unroll
-  for (int k = 1; k < P; k++) w[P - k] = unpack_raw<IN16>(load_raw<IN16>(prm, base - k * Ml));
-  for (long long i0 = 0; i0 < sp.count; i0 += P) {
-    uint32_t raw[P];
-    const long long lo = base + i0 * Ml;
-    if (lo >= prm.in_base && lo + (P - 1) * Ml < in_end) {   // interior tile: plain coalesced loads
+  // P raw words at lo, lo+M, ...: unconditional coalesced loads when the whole tile lies inside this
+  // call's input (every tile but the first/last few of a call), guarded loads otherwise.
+  auto load_tile = [&](long long lo, uint32_t (&raw)[P]) {
+    if (lo >= prm.in_base && lo + (P - 1) * Ml < in_end) {
       #pragma unroll
       for (int ii = 0; ii < P; ii++) raw[ii] = __ldg(inp + (lo + ii * Ml));
     } else {
       #pragma unroll
       for (int ii = 0; ii < P; ii++) raw[ii] = load_raw<IN16>(prm, lo + ii * Ml);
     }
+  };
+  // warm-up rows -P..-1 and tile 0 are requested back to back so their latencies overlap
+  uint32_t wraw[P], raw[P];
+  load_tile(base - P * Ml, wraw);
+  load_tile(base, raw);
+  #pragma unroll
+  for (int k = 1; k < P; k++) w[P - k] = unpack_raw<IN16>(wraw[P - k]);   // row -k sits in slot P-k
+  w[0] = make_float2(0.f, 0.f);
+  for (long long i0 = 0; i0 < sp.count; i0 += P) {
+    // request the next tile now: it is consumed one iteration later, after this tile's FIR and FFT
+    uint32_t nxt[P];
+    if (i0 + P < sp.count) {
+      load_tile(base + (i0 + P) * Ml, nxt);
+    } else {
+      #pragma unroll
+      for (int ii = 0; ii < P; ii++) nxt[ii] = 0u;
+    }
     #pragma unroll
     for (int ii = 0; ii < P; ii++) {
       w[ii] = unpack_raw<IN16>(raw[ii]);
-      float2 acc = __fmul2_rn(hh[0], w[ii]);
+      // two interleaved partial sums (even / odd taps) halve the dependent FMA chain
+      float2 a0 = __fmul2_rn(make_float2(h[0], h[0]), w[ii]);
+      float2 a1 = P > 1 ? __fmul2_rn(make_float2(h[1], h[1]), w[(ii - 1 + P) % P]) : make_float2(0.f, 0.f);
       #pragma unroll
-      for (int q = 1; q < P; q++) acc = __ffma2_rn(hh[q], w[(ii - q + P) % P], acc);
-      emit((int)ii, i0 + ii, acc);
+      for (int q = 2; q < P; q += 2) {
+        a0 = __ffma2_rn(make_float2(h[q], h[q]), w[(ii - q + P) % P], a0);
+        if (q + 1 < P) a1 = __ffma2_rn(make_float2(h[q + 1], h[q + 1]), w[(ii - q - 1 + 2 * P) % P], a1);
+      }
+      emit((int)ii, i0 + ii, __fadd2_rn(a0, a1));
     }
+    #pragma unroll
+    for (int ii = 0; ii < P; ii++) raw[ii] = nxt[ii];
   }
 }
 
@@ -166,7 +187,7 @@ __global__ void __launch_bounds__(NT) k_fft_rows(const float2* __restrict__ u, f
     __syncthreads();
     for (int e = threadIdx.x; e < ROWS * M; e += NT) {
       const int row = e / M, i = e - row * M;
-      buf0[row * S + padi(i)] = row < vrows ? u[(r0 + row) * M + i] : make_float2(0.f, 0.f);
+      buf0[row * S + padi<M>(i)] = row < vrows ? u[(r0 + row) * M + i] : make_float2(0.f, 0.f);
     }
     __syncthreads();
     fft_tile_to_global<M>(buf0, buf1, tw, ROWS, threadIdx.x, NT, y + r0 * M, (long long)M, vrows,
@@ -207,7 +228,7 @@ __global__ void __launch_bounds__(FusedCfg<M, P>::NT) k_chan_fused(ChanParams pr
   for (long long s = (long long)blockIdx.x * G + g; s < nspans; s += (long long)gridDim.x * G) {
     const Span sp = make_span(prm, s);
     if (sp.count <= 0) continue;                      // the whole group takes the same branch
-    const int r = padi((p - sp.shift + M) % M);
+    const int r = padi<M>((p - sp.shift + M) % M);
     float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
     fir_span<P, IN16>(prm, sp, p, [&](int ii, long long i, float2 v) {
       buf0[(ii % RT) * S + r] = v;
