@@ -122,66 +122,92 @@ template <int M> struct RowStride {
   static constexpr int value = M == 32 ? 36 : (M == 64 ? 72 : M + M / 16 + (M < 16 ? 1 : 0));
 };
 
-// One Stockham pass of radix R over `rows` rows of length M held in shared memory.
-//   src/dst : [rows][RowStride<M>] float2 (padded with padi)
-//   Ns      : product of the radices of earlier passes
+// One Stockham pass of radix R over ROWS rows of length M held in shared memory, NT threads.
+//   src/dst : [ROWS][RowStride<M>] float2 (padded with padi)
+//   NS      : product of the radices of earlier passes
 //   LAST    : write to global memory (gout + row*grow_stride + k) instead of dst; rows >= vrows skipped
-// Threads `t` of `nt` cooperate; consecutive threads take consecutive butterflies of a row.
-template <int M, int R, bool LAST>
+//   TWREG   : inter-pass twiddles come from twr[q-1] (registers, loaded once per thread by the caller;
+//             valid when NT is a multiple of M/R so a thread always owns the same butterfly column)
+// Everything about the geometry is a compile-time constant, so after unrolling each access is one
+// per-thread base address plus an immediate offset.
+template <int M, int R, int NS, int ROWS, int NT, bool LAST, bool TWREG>
 __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, float2* __restrict__ dst,
-                                              const float2* __restrict__ tw, int Ns, int rows, int t, int nt,
+                                              const float2* __restrict__ tw, const float2* twr, int t,
                                               float2* __restrict__ gout, long long grow_stride, int vrows) {
   constexpr int S = RowStride<M>::value;
-  constexpr int BPR = M / R;   // butterflies per row
-  const int total = rows * BPR;
-  for (int b = t; b < total; b += nt) {
-    const int row = b / BPR, j = b - row * BPR;
+  constexpr int BPR = M / R;            // butterflies per row
+  constexpr int TOTAL = ROWS * BPR;
+  constexpr int ITERS = (TOTAL + NT - 1) / NT;
+  #pragma unroll
+  for (int it = 0; it < ITERS; it++) {
+    const int b = t + it * NT;
+    if (TOTAL % NT != 0 && b >= TOTAL) break;
+    const int row = b / BPR, j = b % BPR;
     const float2* s = src + row * S;
     float2 v[R];
     #pragma unroll
     for (int q = 0; q < R; q++) v[q] = s[padi<M>(j + q * BPR)];
-    const int k = j & (Ns - 1);   // j mod Ns (Ns is a power of two)
-    if (Ns > 1) {
-      const int tstep = (M / R) / Ns;   // table stride: W_{Ns R}^{q k} = W_M^{q k M/(Ns R)}
+    const int k = j & (NS - 1);         // j mod NS
+    if (NS > 1) {
+      constexpr int tstep = (M / R) / NS;   // W_{NS R}^{q k} = W_M^{q k M/(NS R)}
       #pragma unroll
-      for (int q = 1; q < R; q++) v[q] = cmul(v[q], tw[q * k * tstep]);
+      for (int q = 1; q < R; q++) v[q] = cmul(v[q], TWREG ? twr[q - 1] : tw[q * k * tstep]);
     }
     dft<R>(v);
-    const int j0 = (j - k) * R + k;   // (j / Ns) * Ns * R + k
+    const int j0 = (j - k) * R + k;     // (j / NS) * NS * R + k
     if (LAST) {
       if (row < vrows) {
         float2* g = gout + (long long)row * grow_stride;
         #pragma unroll
-        for (int q = 0; q < R; q++) g[j0 + q * Ns] = v[q];
+        for (int q = 0; q < R; q++) g[j0 + q * NS] = v[q];
       }
     } else {
       float2* d = dst + row * S;
       #pragma unroll
-      for (int q = 0; q < R; q++) d[padi<M>(j0 + q * Ns)] = v[q];
+      for (int q = 0; q < R; q++) d[padi<M>(j0 + q * NS)] = v[q];
     }
   }
 }
 
-// Full M-point FFT (exponent +j) of `rows` rows.  buf0 holds the input (padded layout); buf1 is
-// scratch of the same size.  Result goes to global memory in natural order.  `sync()` must
+// Can the last pass keep its twiddles in registers?  (two-pass plans with a small last radix)
+template <int M, int NT> struct TwReg {
+  typedef Plan<M> PL;
+  static constexpr int RL = PL::np == 2 ? PL::r1 : 1;                 // radix of the last pass
+  static constexpr bool value = PL::np == 2 && RL <= 8 && (NT % (M / RL) == 0);
+  static constexpr int count = value ? RL - 1 : 1;
+};
+// Per-thread twiddles of the last pass of a two-pass plan: W_M^{q * (j mod r0) * (M/(r1 r0))}, q = 1..r1-1
+template <int M, int NT>
+__device__ __forceinline__ void load_last_pass_twiddles(const float2* __restrict__ tw_g, int t, float2* twr) {
+  typedef Plan<M> PL;
+  if constexpr (TwReg<M, NT>::value) {
+    constexpr int R = PL::r1, NS = PL::r0, BPR = M / R, tstep = (M / R) / NS;
+    const int k = (t % BPR) & (NS - 1);
+    #pragma unroll
+    for (int q = 1; q < R; q++) twr[q - 1] = tw_g[q * k * tstep];
+  }
+}
+
+// Full M-point FFT (exponent +j) of ROWS rows by NT threads.  buf0 holds the input (padded layout);
+// buf1 is scratch of the same size.  Result goes to global memory in natural order.  `sync()` must
 // synchronise exactly the threads that cooperate on this tile.
-template <int M, typename SyncF>
-__device__ __forceinline__ void fft_tile_to_global(float2* buf0, float2* buf1, const float2* tw, int rows, int t,
-                                                   int nt, float2* gout, long long grow_stride, int vrows,
+template <int M, int ROWS, int NT, bool TWREG, typename SyncF>
+__device__ __forceinline__ void fft_tile_to_global(float2* buf0, float2* buf1, const float2* tw, const float2* twr,
+                                                   int t, float2* gout, long long grow_stride, int vrows,
                                                    SyncF sync) {
   typedef Plan<M> PL;
   if constexpr (PL::np == 1) {
-    stockham_pass<M, PL::r0, true>(buf0, buf1, tw, 1, rows, t, nt, gout, grow_stride, vrows);
+    stockham_pass<M, PL::r0, 1, ROWS, NT, true, false>(buf0, buf1, tw, twr, t, gout, grow_stride, vrows);
   } else if constexpr (PL::np == 2) {
-    stockham_pass<M, PL::r0, false>(buf0, buf1, tw, 1, rows, t, nt, gout, grow_stride, vrows);
+    stockham_pass<M, PL::r0, 1, ROWS, NT, false, false>(buf0, buf1, tw, twr, t, gout, grow_stride, vrows);
     sync();
-    stockham_pass<M, PL::r1, true>(buf1, buf0, tw, PL::r0, rows, t, nt, gout, grow_stride, vrows);
+    stockham_pass<M, PL::r1, PL::r0, ROWS, NT, true, TWREG>(buf1, buf0, tw, twr, t, gout, grow_stride, vrows);
   } else {
-    stockham_pass<M, PL::r0, false>(buf0, buf1, tw, 1, rows, t, nt, gout, grow_stride, vrows);
+    stockham_pass<M, PL::r0, 1, ROWS, NT, false, false>(buf0, buf1, tw, twr, t, gout, grow_stride, vrows);
     sync();
-    stockham_pass<M, PL::r1, false>(buf1, buf0, tw, PL::r0, rows, t, nt, gout, grow_stride, vrows);
+    stockham_pass<M, PL::r1, PL::r0, ROWS, NT, false, false>(buf1, buf0, tw, twr, t, gout, grow_stride, vrows);
     sync();
-    stockham_pass<M, PL::r2, true>(buf0, buf1, tw, PL::r0 * PL::r1, rows, t, nt, gout, grow_stride, vrows);
+    stockham_pass<M, PL::r2, PL::r0 * PL::r1, ROWS, NT, true, false>(buf0, buf1, tw, twr, t, gout, grow_stride, vrows);
   }
 }
 

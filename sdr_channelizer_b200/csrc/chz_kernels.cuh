@@ -72,47 +72,47 @@ __device__ __forceinline__ Span make_span(const ChanParams& p, long long sp) {
 // u_p[m] = sum_q h[qM+p] x[mD - qM - p].  The P taps of a branch and its last P samples live in
 // registers; a new row costs one 4-byte (int16) or 2-byte (int8) coalesced load and P packed FMAs
 // (fma.rn.f32x2 on (re,im) with the tap duplicated).  `emit(i, value)` receives row i of the span.
-template <int P, bool IN16, typename Emit>
+// MT: number of channels when known at compile time (fused kernel), 0 = take prm.M.
+template <int P, bool IN16, int MT, typename Emit>
 __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, int p, Emit emit) {
   typedef typename RawT<IN16>::type raw_t;
+  const long long Ml = MT ? MT : prm.M;
   float h[P];
   float2 w[P];
   #pragma unroll
-  for (int q = 0; q < P; q++) h[q] = __ldg(prm.taps + q * prm.M + p);
+  for (int q = 0; q < P; q++) h[q] = __ldg(prm.taps + q * Ml + p);
   const long long base = sp.m0 * prm.D - p;   // newest sample of span row 0 for this branch
-  const long long Ml = prm.M;
   const long long in_end = prm.in_base + prm.n_in;
   const raw_t* __restrict__ inp = (const raw_t*)prm.in - prm.in_base;   // inp[idx] for idx in [in_base, in_end)
   // P raw words at lo, lo+M, ...: unconditional coalesced loads when the whole tile lies inside this
   // call's input (every tile but the first/last few of a call), guarded loads otherwise.
   auto load_tile = [&](long long lo, uint32_t (&raw)[P]) {
     if (lo >= prm.in_base && lo + (P - 1) * Ml < in_end) {
+      const raw_t* __restrict__ src = inp + lo;
       #pragma unroll
-      for (int ii = 0; ii < P; ii++) raw[ii] = __ldg(inp + (lo + ii * Ml));
+      for (int ii = 0; ii < P; ii++) raw[ii] = __ldg(src + ii * Ml);
     } else {
       #pragma unroll
       for (int ii = 0; ii < P; ii++) raw[ii] = load_raw<IN16>(prm, lo + ii * Ml);
     }
   };
   // warm-up rows -P..-1 and tile 0 are requested back to back so their latencies overlap
-  uint32_t wraw[P], raw[P];
-  load_tile(base - P * Ml, wraw);
-  load_tile(base, raw);
-  #pragma unroll
-  for (int k = 1; k < P; k++) w[P - k] = unpack_raw<IN16>(wraw[P - k]);   // row -k sits in slot P-k
-  w[0] = make_float2(0.f, 0.f);
+  uint32_t raw[P];
+  {
+    uint32_t wr[P];
+    load_tile(base - P * Ml, wr);
+    load_tile(base, raw);
+    #pragma unroll
+    for (int k = 1; k < P; k++) w[P - k] = unpack_raw<IN16>(wr[P - k]);   // row -k sits in slot P-k
+    w[0] = make_float2(0.f, 0.f);
+  }
   for (long long i0 = 0; i0 < sp.count; i0 += P) {
-    // request the next tile now: it is consumed one iteration later, after this tile's FIR and FFT
-    uint32_t nxt[P];
-    if (i0 + P < sp.count) {
-      load_tile(base + (i0 + P) * Ml, nxt);
-    } else {
-      #pragma unroll
-      for (int ii = 0; ii < P; ii++) nxt[ii] = 0u;
-    }
     #pragma unroll
     for (int ii = 0; ii < P; ii++) {
       w[ii] = unpack_raw<IN16>(raw[ii]);
+      // raw[] is fully consumed at the last row: request the NEXT tile's samples into it now, before
+      // this row's FMAs and the FFT the caller runs in emit(), so the DRAM latency hides behind them.
+      if (ii == P - 1 && i0 + P < sp.count) load_tile(base + (i0 + P) * Ml, raw);
       // two interleaved partial sums (even / odd taps) halve the dependent FMA chain
       float2 a0 = __fmul2_rn(make_float2(h[0], h[0]), w[ii]);
       float2 a1 = P > 1 ? __fmul2_rn(make_float2(h[1], h[1]), w[(ii - 1 + P) % P]) : make_float2(0.f, 0.f);
@@ -123,8 +123,6 @@ __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, 
       }
       emit((int)ii, i0 + ii, __fadd2_rn(a0, a1));
     }
-    #pragma unroll
-    for (int ii = 0; ii < P; ii++) raw[ii] = nxt[ii];
   }
 }
 
@@ -145,7 +143,7 @@ __global__ void __launch_bounds__(128) k_fir(ChanParams prm, float2* __restrict_
     const int r = (p - sp.shift + prm.M) % prm.M;   // u'[r] = u[(r + shift) mod M]
     float2* dst = u + (sp.m0 - prm.row_base) * (long long)prm.M + r;
     const long long rstride = (long long)prm.os * prm.M;
-    fir_span<P, IN16>(prm, sp, p, [&](int, long long i, float2 v) {
+    fir_span<P, IN16, 0>(prm, sp, p, [&](int, long long i, float2 v) {
       if (i < sp.count) dst[i * rstride] = v;
     });
   }
@@ -190,8 +188,8 @@ __global__ void __launch_bounds__(NT) k_fft_rows(const float2* __restrict__ u, f
       buf0[row * S + padi<M>(i)] = row < vrows ? u[(r0 + row) * M + i] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    fft_tile_to_global<M>(buf0, buf1, tw, ROWS, threadIdx.x, NT, y + r0 * M, (long long)M, vrows,
-                          [] { __syncthreads(); });
+    fft_tile_to_global<M, ROWS, NT, false>(buf0, buf1, tw, nullptr, threadIdx.x, y + r0 * M, (long long)M, vrows,
+                                           [] { __syncthreads(); });
   }
 }
 
@@ -213,15 +211,18 @@ template <int M> __device__ __forceinline__ void group_sync(int g) {
 }
 
 template <int M, int P, bool IN16>
-__global__ void __launch_bounds__(FusedCfg<M, P>::NT) k_chan_fused(ChanParams prm) {
+__global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 ? 2 : 1) k_chan_fused(ChanParams prm) {
   extern __shared__ float2 smem[];
   typedef FusedCfg<M, P> CF;
   constexpr int NT = CF::NT, G = CF::G, RT = CF::RT, S = RowStride<M>::value;
+  constexpr bool TWREG = TwReg<M, M>::value;
   float2* tw = smem;                                  // M twiddles
   const int g = threadIdx.x / M, p = threadIdx.x % M;
   float2* buf0 = smem + M + (size_t)g * 2 * RT * S;   // [RT][S]
   float2* buf1 = buf0 + RT * S;
   for (int i = threadIdx.x; i < M; i += NT) tw[i] = prm.tw[i];
+  float2 twr[TwReg<M, M>::count];
+  load_last_pass_twiddles<M, M>(prm.tw, p, twr);
   __syncthreads();
   const long long nspans = prm.spans_per_phase * prm.os;
   const long long rstride = (long long)prm.os * M;
@@ -230,15 +231,15 @@ __global__ void __launch_bounds__(FusedCfg<M, P>::NT) k_chan_fused(ChanParams pr
     if (sp.count <= 0) continue;                      // the whole group takes the same branch
     const int r = padi<M>((p - sp.shift + M) % M);
     float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
-    fir_span<P, IN16>(prm, sp, p, [&](int ii, long long i, float2 v) {
+    fir_span<P, IN16, M>(prm, sp, p, [&](int ii, long long i, float2 v) {
       buf0[(ii % RT) * S + r] = v;
       if (ii % RT == RT - 1) {
         group_sync<M>(g);
         const long long i0 = i - (RT - 1);
         const long long left = sp.count - i0;
         const int vrows = (int)(left < RT ? (left < 0 ? 0 : left) : RT);
-        fft_tile_to_global<M>(buf0, buf1, tw, RT, p, M, gout + i0 * rstride, rstride, vrows,
-                              [&] { group_sync<M>(g); });
+        fft_tile_to_global<M, RT, M, TWREG>(buf0, buf1, tw, twr, p, gout + i0 * rstride, rstride, vrows,
+                                            [&] { group_sync<M>(g); });
         if (Plan<M>::np != 2) group_sync<M>(g);   // the last pass of 1- and 3-pass plans reads buf0
       }
     });
