@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchannelizer.so")
+# CHZ_LIB_PATH lets kernel experiments load an alternative build of the same ABI (never a different backend)
+LIB_PATH = os.environ.get("CHZ_LIB_PATH") or os.path.join(_HERE, "libchannelizer.so")
 
 CHZ_OK = 0
 CHZ_EINVAL, CHZ_EIO, CHZ_EFORMAT, CHZ_EBITWIDTH, CHZ_ESIZE = -1, -2, -3, -4, -5

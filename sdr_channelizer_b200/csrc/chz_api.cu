@@ -26,7 +26,7 @@ struct LaunchPlan { dim3 grid; int span_rows; long long spans_per_phase; };
 static LaunchPlan plan_spans(const ::chz* h, long long nrows, int P, int groups_per_block, int blocks_per_sm,
                              int max_blocks_override = 0) {
   LaunchPlan lp;
-  const long long rows_per_phase = (nrows + h->os - 1) / h->os;
+  const long long rows_per_phase = (nrows + h->os - 1) / h->os + 1;   // +1: a phase may start one row early (make_span)
   const long long max_blocks = max_blocks_override ? max_blocks_override : (long long)h->sm_count * blocks_per_sm;
   const long long total_groups = max_blocks * groups_per_block;
   long long sr = (rows_per_phase + total_groups * 4 - 1) / (total_groups * 4);

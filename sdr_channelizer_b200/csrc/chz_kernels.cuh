@@ -51,19 +51,28 @@ __global__ void k_unpack(const void* __restrict__ in, long long n, float scale, 
 struct Span {
   long long m0;      // first stream row of the span
   long long count;   // rows in the span (stride `os` rows apart)
+  int skip;          // leading rows that are computed but not stored (0 or 1, see make_span)
   int shift;         // (m*D) mod M, the circular branch rotation of these rows (0 or M/2)
 };
+// Rows are filtered in pairs whose two FMA chains visit the taps in different (rotated) orders, so a
+// row's rounding depends on whether it is the first or second of its pair.  To keep results
+// independent of how a recording is cut into calls/shards, pairs are aligned to the GLOBAL row
+// index: when the first row of a phase has an odd global index, the first span starts one row
+// earlier and that extra row is computed but not stored.
 __device__ __forceinline__ Span make_span(const ChanParams& p, long long sp) {
   Span s;
   const int phase_i = (int)(sp % p.os);          // which residue class of rows (relative to row_base)
   const long long si = sp / p.os;
   const long long first = p.row_base + phase_i;   // first row of this class
-  const long long cnt_phase = (p.nrows - phase_i + p.os - 1) / p.os;
+  const int lead = (int)((first / p.os) & 1);     // parity of its global per-phase index
+  const long long cnt_phase = (p.nrows - phase_i + p.os - 1) / p.os + lead;
   const long long i0 = si * (long long)p.span_rows;
-  s.m0 = first + i0 * p.os;
+  s.m0 = first + (i0 - lead) * p.os;
   s.count = cnt_phase - i0;
   if (s.count > p.span_rows) s.count = p.span_rows;
   if (s.count < 0) s.count = 0;
+  s.skip = si == 0 ? lead : 0;
+  if (cnt_phase - lead <= 0) s.count = 0;         // no real row in this phase
   s.shift = (int)((s.m0 * p.D) % p.M);
   return s;
 }
@@ -107,21 +116,29 @@ __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, 
     w[0] = make_float2(0.f, 0.f);
   }
   for (long long i0 = 0; i0 < sp.count; i0 += P) {
+    // Rows are filtered two at a time: two independent P-long FMA chains interleave (ILP 2) with no
+    // extra adds.  Row ii uses slot (ii - q) mod P for tap q.
     #pragma unroll
-    for (int ii = 0; ii < P; ii++) {
+    for (int ii = 0; ii < P; ii += 2) {
       w[ii] = unpack_raw<IN16>(raw[ii]);
-      // raw[] is fully consumed at the last row: request the NEXT tile's samples into it now, before
-      // this row's FMAs and the FFT the caller runs in emit(), so the DRAM latency hides behind them.
-      if (ii == P - 1 && i0 + P < sp.count) load_tile(base + (i0 + P) * Ml, raw);
-      // two interleaved partial sums (even / odd taps) halve the dependent FMA chain
-      float2 a0 = __fmul2_rn(make_float2(h[0], h[0]), w[ii]);
-      float2 a1 = P > 1 ? __fmul2_rn(make_float2(h[1], h[1]), w[(ii - 1 + P) % P]) : make_float2(0.f, 0.f);
+      // tap P-1 of row ii reads the OLDEST sample, which sits in the slot row ii+1 is about to take:
+      // start row ii's chain with it before that slot is overwritten
+      float2 a0 = __fmul2_rn(make_float2(h[P - 1], h[P - 1]), w[(ii + 1) % P]);
+      if (ii + 1 < P) w[ii + 1] = unpack_raw<IN16>(raw[ii + 1]);
+      // raw[] is fully consumed at the last rows: request the NEXT tile's samples into it now, before
+      // these rows' FMAs and the FFT the caller runs in emit(), so the DRAM latency hides behind them.
+      if (ii + 2 >= P && i0 + P < sp.count) load_tile(base + (i0 + P) * Ml, raw);
+      // Row ii+1 walks the same window slots one tap later (q+1), so each step's two FMAs share their
+      // 64-bit window operand (register reuse); its tap order is therefore rotated by one relative to
+      // row ii -- pairs are aligned to global row parity (make_span) to keep that deterministic.
+      float2 a1 = ii + 1 < P ? __fmul2_rn(make_float2(h[0], h[0]), w[ii + 1]) : make_float2(0.f, 0.f);
       #pragma unroll
-      for (int q = 2; q < P; q += 2) {
+      for (int q = 0; q < P - 1; q++) {
         a0 = __ffma2_rn(make_float2(h[q], h[q]), w[(ii - q + P) % P], a0);
-        if (q + 1 < P) a1 = __ffma2_rn(make_float2(h[q + 1], h[q + 1]), w[(ii - q - 1 + 2 * P) % P], a1);
+        if (ii + 1 < P && q + 1 < P) a1 = __ffma2_rn(make_float2(h[q + 1], h[q + 1]), w[(ii - q + P) % P], a1);
       }
-      emit((int)ii, i0 + ii, __fadd2_rn(a0, a1));
+      emit((int)ii, i0 + ii, a0);
+      if (ii + 1 < P) emit((int)ii + 1, i0 + ii + 1, a1);
     }
   }
 }
@@ -144,7 +161,7 @@ __global__ void __launch_bounds__(128) k_fir(ChanParams prm, float2* __restrict_
     float2* dst = u + (sp.m0 - prm.row_base) * (long long)prm.M + r;
     const long long rstride = (long long)prm.os * prm.M;
     fir_span<P, IN16, 0>(prm, sp, p, [&](int, long long i, float2 v) {
-      if (i < sp.count) dst[i * rstride] = v;
+      if (i >= sp.skip && i < sp.count) dst[i * rstride] = v;
     });
   }
 }
@@ -188,7 +205,7 @@ __global__ void __launch_bounds__(NT) k_fft_rows(const float2* __restrict__ u, f
       buf0[row * S + padi<M>(i)] = row < vrows ? u[(r0 + row) * M + i] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    fft_tile_to_global<M, ROWS, NT, false>(buf0, buf1, tw, nullptr, threadIdx.x, y + r0 * M, (long long)M, vrows,
+    fft_tile_to_global<M, ROWS, NT, false>(buf0, buf1, tw, nullptr, threadIdx.x, y + r0 * M, (long long)M, 0, vrows,
                                            [] { __syncthreads(); });
   }
 }
@@ -237,8 +254,9 @@ __global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 
         group_sync<M>(g);
         const long long i0 = i - (RT - 1);
         const long long left = sp.count - i0;
-        const int vrows = (int)(left < RT ? (left < 0 ? 0 : left) : RT);
-        fft_tile_to_global<M, RT, M, TWREG>(buf0, buf1, tw, twr, p, gout + i0 * rstride, rstride, vrows,
+        const int vhi = (int)(left < RT ? (left < 0 ? 0 : left) : RT);       // rows [vlo, vhi) of the tile are stored
+        const int vlo = i0 < sp.skip ? (int)(sp.skip - i0) : 0;
+        fft_tile_to_global<M, RT, M, TWREG>(buf0, buf1, tw, twr, p, gout + i0 * rstride, rstride, vlo, vhi,
                                             [&] { group_sync<M>(g); });
         if (Plan<M>::np != 2) group_sync<M>(g);   // the last pass of 1- and 3-pass plans reads buf0
       }

@@ -102,6 +102,27 @@ def test_channelizer_matches_oracle(orc, M, P, os_, kind, n):
     ch.close()
 
 
+@pytest.mark.parametrize("M,P,os_,path", [(64, 16, 1, 1), (64, 16, 2, 1), (64, 12, 1, 1), (8, 8, 1, 1), (256, 16, 1, 1),
+                                          (512, 8, 2, 1), (32, 12, 2, 1), (128, 16, 1, 1), (16, 16, 1, 1),
+                                          (64, 16, 1, 2), (1024, 16, 2, 0), (4096, 8, 1, 0), (64, 24, 1, 0), (64, 32, 2, 0)])
+def test_random_taps_every_tap_index_matters(orc, M, P, os_, path):
+    """A designed prototype has tiny end taps, which would hide a mis-indexed tap or window slot
+    below the 1e-5 tolerance; with random taps of equal weight any such slip is an O(1/P) error."""
+    _torch()
+    rng = np.random.default_rng(M * 7 + P)
+    taps = (rng.uniform(0.5, 1.0, M * P) * rng.choice([-1.0, 1.0], M * P) / P).astype(np.float32)
+    n = M * (5 * P + 3) * 4 + 11
+    iq, bw = synth.noise_int16_full(n, seed=P)
+    ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=os_)
+    ch.set_option(_lib.CHZ_OPT_FORCE_PATH, path)
+    y = ch(iq, bw)
+    ref = orc.channelize_raw(iq, bw, M, taps.astype(np.float64), os_)
+    assert y.shape == ref.shape
+    assert synth.rel_rms(y, ref) <= 2e-6
+    assert np.max(np.abs(y - ref)) <= 1e-5 * np.max(np.abs(ref))
+    ch.close()
+
+
 @pytest.mark.parametrize("M,P,os_", [(64, 16, 1), (64, 16, 2), (256, 12, 1), (8, 8, 1)])
 def test_split_path_equals_fused_path(M, P, os_):
     _torch()
