@@ -358,6 +358,7 @@ void chz_destroy(chz_t* h) {
   }
   if (h->d_store) cudaFree(h->d_store);
   if (h->d_u) cudaFree(h->d_u);
+  for (chzi::Scratch* sc : {&h->pdw_hist, &h->pdw_sel, &h->pdw_thr, &h->pdw_cnt, &h->pdw_ev, &h->pdw_pin, &h->pdw_pout}) sc->release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);

@@ -23,6 +23,24 @@ void set_cuda_error(cudaError_t e, const char* what, const char* file, int line)
 
 }  // namespace chzi
 
+namespace chzi {
+// Device scratch that lives with the handle and only ever grows: cudaMalloc/cudaFree on every call
+// cost up to tens of milliseconds on a busy driver (measured), far more than the PDW kernels.
+struct Scratch {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+}  // namespace chzi
+
 struct chz {
   int device = 0;
   int sm_count = 148;
@@ -59,6 +77,10 @@ struct chz {
 
   int force_path = 0;
   uint64_t launches = 0;
+
+  // PDW scratch (histograms, select state, thresholds, edge events, pulse lists)
+  chzi::Scratch pdw_hist, pdw_sel, pdw_thr, pdw_cnt, pdw_ev, pdw_pin, pdw_pout;
+  uint64_t pdw_ev_cap = 1ull << 20;
 
   // PDW results of the last run
   std::vector<double> noise_floor;      // natural channel order

@@ -9,7 +9,10 @@
 //   :97-128  per-pulse stats     -> k_pulse_stats: one block per pulse, radix-select medians
 // Input layout: y[row][k], natural channel order, fp32 complex.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "chz_internal.h"
@@ -254,24 +257,33 @@ __global__ void __launch_bounds__(128) k_pulse_stats(const float2* __restrict__ 
 }
 
 // ---- host driver ---------------------------------------------------------------------------------------
-template <typename T> struct DevBuf {
-  T* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
-};
-
 int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t nrows) {
   const int M = (int)h->M;
   cudaStream_t st = h->stream;
+  // CHZ_PDW_TRACE=1: host wall-clock of each stage on stderr (debug aid)
+  static const bool trace = std::getenv("CHZ_PDW_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[chz pdw] %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   h->pdws.clear();
   h->noise_floor.assign(M, NAN);
   if (nrows == 0) return CHZ_OK;
 
   // 1. exact per-channel median of |y| (:73)
-  DevBuf<uint32_t> d_hist; DevBuf<SelState> d_sel;
-  CHZ_CUDA(d_hist.alloc((size_t)M * 2 * kBins));
-  CHZ_CUDA(d_sel.alloc(M));
-  CHZ_CUDA(cudaMemsetAsync(d_hist.p, 0, (size_t)M * 2 * kBins * sizeof(uint32_t), st));
+  CHZ_CUDA(h->pdw_hist.reserve((size_t)M * 2 * kBins * sizeof(uint32_t)));
+  CHZ_CUDA(h->pdw_sel.reserve((size_t)M * sizeof(SelState)));
+  CHZ_CUDA(h->pdw_thr.reserve((size_t)M * sizeof(Thr)));
+  CHZ_CUDA(h->pdw_cnt.reserve(sizeof(unsigned long long)));
+  uint32_t* d_hist = (uint32_t*)h->pdw_hist.p;
+  SelState* d_sel = (SelState*)h->pdw_sel.p;
+  Thr* d_thr = (Thr*)h->pdw_thr.p;
+  unsigned long long* d_cnt = (unsigned long long*)h->pdw_cnt.p;
+  CHZ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)M * 2 * kBins * sizeof(uint32_t), st));
+  lap("alloc");
   const uint32_t rank_lo = (uint32_t)((nrows - 1) / 2), rank_hi = (uint32_t)(nrows / 2);
   long long ychunks = (h->sm_count * 4 + M / 4 - 1) / (M / 4);
   const long long max_chunks = (long long)((nrows + 255) / 256);
@@ -279,15 +291,16 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
   if (ychunks < 1) ychunks = 1;
   if (ychunks > 65535) ychunks = 65535;
   for (int pass = 0; pass < 3; pass++) {
-    k_hist<<<dim3(M / 4, (unsigned)ychunks), 256, 0, st>>>(y, (long long)nrows, M, pass, d_sel.p, d_hist.p);
-    k_select<<<M, 256, 0, st>>>(d_hist.p, d_sel.p, pass, rank_lo, rank_hi);
+    k_hist<<<dim3(M / 4, (unsigned)ychunks), 256, 0, st>>>(y, (long long)nrows, M, pass, d_sel, d_hist);
+    k_select<<<M, 256, 0, st>>>(d_hist, d_sel, pass, rank_lo, rank_hi);
     h->launches += 2;
   }
   CHZ_CUDA(cudaGetLastError());
   std::vector<SelState> sel(M);
-  CHZ_CUDA(cudaMemcpyAsync(sel.data(), d_sel.p, sizeof(SelState) * M, cudaMemcpyDeviceToHost, st));
+  CHZ_CUDA(cudaMemcpyAsync(sel.data(), d_sel, sizeof(SelState) * M, cudaMemcpyDeviceToHost, st));
   CHZ_CUDA(cudaStreamSynchronize(st));
 
+  lap("median");
   // 2. thresholds (:74-75), double on the host, bracketed by floats for the fp32 comparisons
   const double scale = std::pow(10.0, prm->snr_threshold_db / 10.0);
   std::vector<Thr> thr(M);
@@ -304,9 +317,7 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
     else if ((double)f > t) le = std::nextafterf(f, -INFINITY);
     thr[k].ge = ge; thr[k].le = le;
   }
-  DevBuf<Thr> d_thr;
-  CHZ_CUDA(d_thr.alloc(M));
-  CHZ_CUDA(cudaMemcpyAsync(d_thr.p, thr.data(), sizeof(Thr) * M, cudaMemcpyHostToDevice, st));
+  CHZ_CUDA(cudaMemcpyAsync(d_thr, thr.data(), sizeof(Thr) * M, cudaMemcpyHostToDevice, st));
 
   // 3. edge events (:79-96)
   const int chunk_rows = 64;
@@ -314,27 +325,29 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
   const int lanes_ch = M < 32 ? M : 32, streams = 32 / lanes_ch, ch_groups = (M + 31) / 32;
   const long long warps = ((nchunks + streams - 1) / streams) * ch_groups;
   const long long blocks = (warps + 7) / 8;
-  unsigned long long cap = 1ull << 20, nev = 0;
-  DevBuf<unsigned long long> d_cnt;
-  CHZ_CUDA(d_cnt.alloc(1));
+  unsigned long long nev = 0;
   std::vector<unsigned long long> ev;
   for (;;) {
-    DevBuf<unsigned long long> d_ev;
-    CHZ_CUDA(d_ev.alloc(cap));
-    CHZ_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), st));
-    k_detect<<<(unsigned)blocks, 256, 0, st>>>(y, (long long)nrows, M, d_thr.p, chunk_rows, d_ev.p, cap, d_cnt.p);
+    const unsigned long long cap = h->pdw_ev_cap;
+    CHZ_CUDA(h->pdw_ev.reserve(cap * sizeof(unsigned long long)));
+    unsigned long long* d_ev = (unsigned long long*)h->pdw_ev.p;
+    CHZ_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
+    k_detect<<<(unsigned)blocks, 256, 0, st>>>(y, (long long)nrows, M, d_thr, chunk_rows, d_ev, cap, d_cnt);
     h->launches++;
     CHZ_CUDA(cudaGetLastError());
-    CHZ_CUDA(cudaMemcpyAsync(&nev, d_cnt.p, sizeof nev, cudaMemcpyDeviceToHost, st));
+    CHZ_CUDA(cudaMemcpyAsync(&nev, d_cnt, sizeof nev, cudaMemcpyDeviceToHost, st));
     CHZ_CUDA(cudaStreamSynchronize(st));
     if (nev <= cap) {
       ev.resize(nev);
-      if (nev) CHZ_CUDA(cudaMemcpy(ev.data(), d_ev.p, nev * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      if (nev) {
+        CHZ_CUDA(cudaMemcpyAsync(ev.data(), d_ev, nev * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CHZ_CUDA(cudaStreamSynchronize(st));
+      }
       break;
     }
-    cap = nev;   // rerun with room for everything
+    h->pdw_ev_cap = nev + nev / 4;   // rerun with room for everything
   }
-
+  lap("detect");
   // 4. pair edges per channel in time order; a pulse still open at the end is dropped (:135)
   std::sort(ev.begin(), ev.end());
   std::vector<PulseIn> pulses;
@@ -354,18 +367,21 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
   }
   if (pulses.empty()) return CHZ_OK;
 
+  lap("pair");
   // 5. per-pulse medians and saturation (:97-122)
-  DevBuf<PulseIn> d_pin; DevBuf<PulseOut> d_pout;
-  CHZ_CUDA(d_pin.alloc(pulses.size()));
-  CHZ_CUDA(d_pout.alloc(pulses.size()));
-  CHZ_CUDA(cudaMemcpyAsync(d_pin.p, pulses.data(), pulses.size() * sizeof(PulseIn), cudaMemcpyHostToDevice, st));
-  k_pulse_stats<<<(unsigned)pulses.size(), 128, 0, st>>>(y, M, prm->sat_level, d_pin.p, d_pout.p);
+  CHZ_CUDA(h->pdw_pin.reserve(pulses.size() * sizeof(PulseIn)));
+  CHZ_CUDA(h->pdw_pout.reserve(pulses.size() * sizeof(PulseOut)));
+  PulseIn* d_pin = (PulseIn*)h->pdw_pin.p;
+  PulseOut* d_pout = (PulseOut*)h->pdw_pout.p;
+  CHZ_CUDA(cudaMemcpyAsync(d_pin, pulses.data(), pulses.size() * sizeof(PulseIn), cudaMemcpyHostToDevice, st));
+  k_pulse_stats<<<(unsigned)pulses.size(), 128, 0, st>>>(y, M, prm->sat_level, d_pin, d_pout);
   h->launches++;
   CHZ_CUDA(cudaGetLastError());
   std::vector<PulseOut> pout(pulses.size());
-  CHZ_CUDA(cudaMemcpyAsync(pout.data(), d_pout.p, pulses.size() * sizeof(PulseOut), cudaMemcpyDeviceToHost, st));
+  CHZ_CUDA(cudaMemcpyAsync(pout.data(), d_pout, pulses.size() * sizeof(PulseOut), cudaMemcpyDeviceToHost, st));
   CHZ_CUDA(cudaStreamSynchronize(st));
 
+  lap("stats");
   // 6. records (:97-128), already in the reference's order: shifted channel ascending, then time
   const double fs_dec = prm->fs_sps / (double)h->D;        // :62
   h->pdws.resize(pulses.size());
