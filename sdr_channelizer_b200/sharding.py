@@ -32,8 +32,8 @@ def plan_time_shards(num_samples, M, ntaps, oversample, world_size):
     """Split floor(num_samples / D) rows into world_size contiguous ranges.
 
     Each shard starts feeding at a frame boundary at least (taps-1) samples before its first owned
-    row's newest sample, rounded down to a multiple of M so the circular branch rotation (m*D mod M)
-    restarts in phase.  Rows the halo itself produces are discarded (their FIR history is incomplete).
+    row's newest sample, rounded down to a multiple of 2*M so the circular branch rotation (m*D mod M)
+    restarts in phase and global row parity is preserved.  Rows the halo itself produces are discarded (their FIR history is incomplete).
     """
     D = M // oversample
     total_rows = num_samples // D
@@ -46,7 +46,10 @@ def plan_time_shards(num_samples, M, ntaps, oversample, world_size):
         row = re
         # newest sample of row rb is rb*D; oldest it touches is rb*D - (ntaps-1)
         start = max(0, rb * D - (ntaps - 1))
-        start = (start // M) * M                      # frame- and rotation-aligned
+        # aligned to 2*M samples: frames and the circular rotation (m*D mod M) restart in phase, and a
+        # row keeps the parity of its global index, which fixes the tap order the kernel sums it in
+        # (rows are filtered in pairs) -> shard results are bit-identical to the unsharded run
+        start = (start // (2 * M)) * (2 * M)
         discard = rb - start // D                     # rows start//D .. rb-1 come out of the halo
         shards.append(TimeShard(r, rb, re, start, re * D, discard))
     return shards

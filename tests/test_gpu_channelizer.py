@@ -159,6 +159,26 @@ def test_streaming_chunks_are_bit_identical_to_one_shot(M, P, os_):
     ch.close()
 
 
+@pytest.mark.parametrize("M,P,os_,world", [(64, 16, 1, 2), (64, 16, 1, 8), (1024, 16, 2, 4), (4096, 16, 1, 8), (256, 12, 2, 3)])
+def test_time_shards_bit_identical_to_unsharded(M, P, os_, world):
+    """configs[3] scaling path on one GPU: each shard (halo of taps-1 samples fed first, its rows
+    discarded) reproduces exactly the rows of the unsharded run, so stitching is a plain concatenation."""
+    _torch()
+    n = M * 150 * world + 3 * M + 1
+    iq, bw = synth.tones_int16_q11(n, M, seed=13)
+    taps = pkg.design_prototype(M, P)
+    ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=os_)
+    whole = ch(iq, bw).copy()
+    parts = []
+    for sh in pkg.plan_time_shards(n, M, M * P, os_, world):
+        ch.reset()
+        parts.append(ch(iq[sh.sample_begin:sh.sample_end], bw)[sh.discard_rows:].copy())
+        assert parts[-1].shape[0] == sh.rows
+    got = pkg.stitch_rows(parts)
+    assert got.shape == whole.shape and np.array_equal(got.view(np.float32), whole.view(np.float32))
+    ch.close()
+
+
 def test_host_chunked_pipeline_equals_single_chunk():
     _torch()
     M = 64
