@@ -1,7 +1,9 @@
 // libchannelizer: C ABI implementation (handles, streaming state, launches, host pipeline).
 // See include/channelizer.h for the contract and the reference lines each entry point replaces.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -64,18 +66,30 @@ static int launch_fused(::chz* h, ChanParams prm, cudaStream_t st) {
   return CHZ_OK;
 }
 
-template <int P, bool IN16>
-static int launch_fir(::chz* h, ChanParams prm, float2* u, cudaStream_t st) {
+template <int P, bool IN16, int MT>
+static int launch_fir_m(::chz* h, ChanParams prm, float2* u, cudaStream_t st) {
   const int bpb = prm.M < 128 ? prm.M : 128, nbb = prm.M / bpb, groups = 128 / bpb;
-  // blocks per SM by registers: 128 threads, <= ~96 regs -> 5; keep 4 resident per SM and branch block
+  // 128 threads x <= 128 registers: 4 blocks resident per SM; span blocks per branch block = SMs*4 / nbb
   LaunchPlan lp = plan_spans(h, prm.nrows, P, groups, 4, (h->sm_count * 4 / nbb) > 0 ? (h->sm_count * 4 / nbb) : 1);
   prm.span_rows = lp.span_rows;
   prm.spans_per_phase = lp.spans_per_phase;
   const unsigned grid = lp.grid.x * (unsigned)nbb;
-  k_fir<P, IN16><<<grid, 128, 0, st>>>(prm, u);
+  k_fir<P, IN16, MT><<<grid, 128, 0, st>>>(prm, u);
   h->launches++;
   CHZ_CUDA(cudaGetLastError());
   return CHZ_OK;
+}
+template <int P, bool IN16>
+static int launch_fir(::chz* h, const ChanParams& prm, float2* u, cudaStream_t st) {
+  if (P == 16 || P == 12) {   // the large-M sizes the split path exists for get compile-time strides
+    switch (prm.M) {
+      case 1024: return launch_fir_m<P, IN16, (P == 16 || P == 12) ? 1024 : 0>(h, prm, u, st);
+      case 2048: return launch_fir_m<P, IN16, (P == 16 || P == 12) ? 2048 : 0>(h, prm, u, st);
+      case 4096: return launch_fir_m<P, IN16, (P == 16 || P == 12) ? 4096 : 0>(h, prm, u, st);
+      default: break;
+    }
+  }
+  return launch_fir_m<P, IN16, 0>(h, prm, u, st);
 }
 
 template <int M, int ROWS, int NT>
@@ -99,6 +113,27 @@ static int launch_fft_rows_t(::chz* h, const float2* u, float2* y, long long nro
   return CHZ_OK;
 }
 
+template <int M, int ROWS>
+static int launch_fft_rows_big(::chz* h, const float2* u, float2* y, long long nrows, cudaStream_t st) {
+  auto kern = k_fft_rows_big<M, ROWS>;
+  const size_t smem = (size_t)(2 * ROWS * RowStride<M>::value) * sizeof(float2);
+  static thread_local int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CHZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, smem));
+    blocks_per_sm = nb > 0 ? nb : 1;
+  }
+  long long blocks = (nrows + ROWS - 1) / ROWS;
+  const long long maxb = (long long)h->sm_count * blocks_per_sm;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) return CHZ_OK;
+  kern<<<(unsigned)blocks, 256, smem, st>>>(u, y, h->d_tw, nrows);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  return CHZ_OK;
+}
+
 static int launch_fft_rows(::chz* h, const float2* u, float2* y, long long nrows, cudaStream_t st) {
   switch (h->M) {
     case 8: return launch_fft_rows_t<8, 256, 256>(h, u, y, nrows, st);
@@ -107,10 +142,10 @@ static int launch_fft_rows(::chz* h, const float2* u, float2* y, long long nrows
     case 64: return launch_fft_rows_t<64, 32, 256>(h, u, y, nrows, st);
     case 128: return launch_fft_rows_t<128, 16, 256>(h, u, y, nrows, st);
     case 256: return launch_fft_rows_t<256, 16, 256>(h, u, y, nrows, st);
-    case 512: return launch_fft_rows_t<512, 8, 256>(h, u, y, nrows, st);
-    case 1024: return launch_fft_rows_t<1024, 4, 256>(h, u, y, nrows, st);
-    case 2048: return launch_fft_rows_t<2048, 2, 256>(h, u, y, nrows, st);
-    case 4096: return launch_fft_rows_t<4096, 1, 256>(h, u, y, nrows, st);
+    case 512: return launch_fft_rows_big<512, 8>(h, u, y, nrows, st);
+    case 1024: return launch_fft_rows_big<1024, 4>(h, u, y, nrows, st);
+    case 2048: return launch_fft_rows_big<2048, 2>(h, u, y, nrows, st);
+    case 4096: return launch_fft_rows_big<4096, 1>(h, u, y, nrows, st);
     default: return CHZ_EINVAL;
   }
 }
@@ -197,11 +232,26 @@ static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, 
       if (rc == 1) return CHZ_EINVAL;
       if (rc) return rc;
     } else {
-      // split path: FIR rows -> the output buffer itself (in place), then the row FFT over it
-      rc = in16 ? launch_fir_dispatch<true>(h, prm, out_dev, st) : launch_fir_dispatch<false>(h, prm, out_dev, st);
-      if (rc) return rc;
-      rc = launch_fft_rows(h, out_dev, out_dev, (long long)rows_new, st);
-      if (rc) return rc;
+      // split path: FIR rows -> the output buffer itself, then the row FFT over it IN PLACE.  The
+      // recording is walked in row chunks small enough that a chunk's FIR output is still in the 126 MB
+      // L2 when the FFT kernel reads it and overwrites it with the final rows: the intermediate then
+      // never travels to DRAM, which keeps traffic near the fused kernel's 4 + 8 B per sample instead
+      // of 4 + 8 + 8 + 8.
+      long long chunk_rows = (long long)(h->split_chunk_bytes / ((uint64_t)h->M * sizeof(float2)));
+      chunk_rows &= ~1LL;                       // even: row pairs stay aligned to global parity
+      if (chunk_rows < 2) chunk_rows = 2;
+      for (long long r0 = 0; r0 < (long long)rows_new; r0 += chunk_rows) {
+        const long long nr = std::min<long long>(chunk_rows, (long long)rows_new - r0);
+        ChanParams cp = prm;
+        cp.row_base = prm.row_base + r0;
+        cp.nrows = nr;
+        float2* dst = out_dev + r0 * (long long)h->M;
+        cp.out = dst;
+        rc = in16 ? launch_fir_dispatch<true>(h, cp, dst, st) : launch_fir_dispatch<false>(h, cp, dst, st);
+        if (rc) return rc;
+        rc = launch_fft_rows(h, dst, dst, nr, st);
+        if (rc) return rc;
+      }
     }
   }
   // history for the next call: everything from the oldest sample the next row can touch
@@ -325,13 +375,37 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
     CHZ_TRY(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
     CHZ_TRY(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
   }
-  std::vector<float2> tw(M);
-  for (uint32_t i = 0; i < M; i++) {
-    const double a = 2.0 * 3.14159265358979323846264338327950288 * (double)i / (double)M;
-    tw[i] = make_float2((float)std::cos(a), (float)std::sin(a));
+  // Inter-pass twiddles of the Stockham plan (same radices as Plan<M> on the device), laid out per pass
+  // as entry (q-1)*NS + k = W_{NS R}^{q k} = e^{+j 2 pi q k / (NS R)} so a warp reads consecutive k.
+  std::vector<float2> tw(M, make_float2(1.f, 0.f));
+  {
+    int r[3] = {1, 1, 1};
+    switch (M) {
+      case 8: r[0] = 8; break;              case 16: r[0] = 16; break;
+      case 32: r[0] = 8; r[1] = 4; break;   case 64: r[0] = 8; r[1] = 8; break;
+      case 128: r[0] = 16; r[1] = 8; break; case 256: r[0] = 16; r[1] = 16; break;
+      case 512: r[0] = 16; r[1] = 8; r[2] = 4; break;   case 1024: r[0] = 16; r[1] = 8; r[2] = 8; break;
+      case 2048: r[0] = 16; r[1] = 16; r[2] = 8; break; case 4096: r[0] = 16; r[1] = 16; r[2] = 16; break;
+    }
+    size_t off = 0;
+    int ns = r[0];
+    for (int pass = 1; pass < 3 && r[pass] > 1; pass++) {
+      const int R = r[pass];
+      for (int q = 1; q < R; q++)
+        for (int k = 0; k < ns; k++) {
+          const double a = 2.0 * 3.14159265358979323846264338327950288 * (double)q * (double)k / ((double)ns * R);
+          tw[off + (size_t)(q - 1) * ns + k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+      off += (size_t)(R - 1) * ns;
+      ns *= R;
+    }
   }
   CHZ_TRY(cudaMalloc(&h->d_tw, sizeof(float2) * M));
   CHZ_TRY(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+  if (const char* e = std::getenv("CHZ_SPLIT_CHUNK_MB")) {   // tuning aid
+    const long v = std::atol(e);
+    if (v > 0) h->split_chunk_bytes = (uint64_t)v << 20;
+  }
   h->hist_cap = (uint64_t)h->L + h->D + 16;
   for (int i = 0; i < 2; i++) {
     CHZ_TRY(cudaMalloc(&h->d_hist[i], h->hist_cap * 4));

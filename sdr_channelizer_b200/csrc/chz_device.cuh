@@ -144,9 +144,11 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, fl
     for (int q = 0; q < R; q++) v[q] = s[padi<M>(j + q * BPR)];
     const int k = j & (NS - 1);         // j mod NS
     if (NS > 1) {
-      constexpr int tstep = (M / R) / NS;   // W_{NS R}^{q k} = W_M^{q k M/(NS R)}
+      // twiddle table layout (host: build_twiddles): per pass, entry (q-1)*NS + k holds
+      // W_{NS R}^{q k}; the lanes of a warp read consecutive k -> consecutive addresses, no conflicts
+      constexpr int TWOFF = (NS == Plan<M>::r0) ? 0 : (Plan<M>::r1 - 1) * Plan<M>::r0;
       #pragma unroll
-      for (int q = 1; q < R; q++) v[q] = cmul(v[q], TWREG ? twr[q - 1] : tw[q * k * tstep]);
+      for (int q = 1; q < R; q++) v[q] = cmul(v[q], TWREG ? twr[q - 1] : tw[TWOFF + (q - 1) * NS + k]);
     }
     dft<R>(v);
     const int j0 = (j - k) * R + k;     // (j / NS) * NS * R + k
@@ -171,15 +173,15 @@ template <int M, int NT> struct TwReg {
   static constexpr bool value = PL::np == 2 && RL <= 8 && (NT % (M / RL) == 0);
   static constexpr int count = value ? RL - 1 : 1;
 };
-// Per-thread twiddles of the last pass of a two-pass plan: W_M^{q * (j mod r0) * (M/(r1 r0))}, q = 1..r1-1
+// Per-thread twiddles of the last pass of a two-pass plan: W_{r0 r1}^{q (j mod r0)}, q = 1..r1-1
 template <int M, int NT>
 __device__ __forceinline__ void load_last_pass_twiddles(const float2* __restrict__ tw_g, int t, float2* twr) {
   typedef Plan<M> PL;
   if constexpr (TwReg<M, NT>::value) {
-    constexpr int R = PL::r1, NS = PL::r0, BPR = M / R, tstep = (M / R) / NS;
+    constexpr int R = PL::r1, NS = PL::r0, BPR = M / R;
     const int k = (t % BPR) & (NS - 1);
     #pragma unroll
-    for (int q = 1; q < R; q++) twr[q - 1] = tw_g[q * k * tstep];
+    for (int q = 1; q < R; q++) twr[q - 1] = tw_g[(q - 1) * NS + k];
   }
 }
 

@@ -76,6 +76,7 @@ struct chz {
   int64_t chunk_rows = 0;
 
   int force_path = 0;
+  uint64_t split_chunk_bytes = 1ull << 40;    // split path: FIR output bytes per launch pair (CHZ_SPLIT_CHUNK_MB)
   uint64_t launches = 0;
 
   // PDW scratch (histograms, select state, thresholds, edge events, pulse lists)

@@ -2,6 +2,8 @@
 // Reference math replaced: matlab/create_pdws_channelized.m:35-38 (normalise) and :57
 // (iq = channelizer(iq), MathWorks dsp.Channelizer — closed source; definition in DESIGN.md).
 #pragma once
+#include <type_traits>
+
 #include "chz_device.cuh"
 
 namespace chzi {
@@ -82,7 +84,7 @@ __device__ __forceinline__ Span make_span(const ChanParams& p, long long sp) {
 // registers; a new row costs one 4-byte (int16) or 2-byte (int8) coalesced load and P packed FMAs
 // (fma.rn.f32x2 on (re,im) with the tap duplicated).  `emit(i, value)` receives row i of the span.
 // MT: number of channels when known at compile time (fused kernel), 0 = take prm.M.
-template <int P, bool IN16, int MT, typename Emit>
+template <int P, bool IN16, int MT, bool EARLY, typename Emit>
 __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, int p, Emit emit) {
   typedef typename RawT<IN16>::type raw_t;
   const long long Ml = MT ? MT : prm.M;
@@ -115,19 +117,21 @@ __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, 
     for (int k = 1; k < P; k++) w[P - k] = unpack_raw<IN16>(wr[P - k]);   // row -k sits in slot P-k
     w[0] = make_float2(0.f, 0.f);
   }
-  for (long long i0 = 0; i0 < sp.count; i0 += P) {
-    // Rows are filtered two at a time: two independent P-long FMA chains interleave (ILP 2) with no
-    // extra adds.  Row ii uses slot (ii - q) mod P for tap q.
+  // One tile = P rows filtered two at a time: two independent P-long FMA chains interleave (ILP 2)
+  // with no extra adds.  Row ii uses slot (ii - q) mod P for tap q.  LATE: re-fill cur[] with the next
+  // tile's samples as soon as its last word is unpacked.
+  auto rows = [&](long long i0, uint32_t (&cur)[P], auto late) {
+    constexpr bool LATE = decltype(late)::value;
     #pragma unroll
     for (int ii = 0; ii < P; ii += 2) {
-      w[ii] = unpack_raw<IN16>(raw[ii]);
+      w[ii] = unpack_raw<IN16>(cur[ii]);
       // tap P-1 of row ii reads the OLDEST sample, which sits in the slot row ii+1 is about to take:
       // start row ii's chain with it before that slot is overwritten
       float2 a0 = __fmul2_rn(make_float2(h[P - 1], h[P - 1]), w[(ii + 1) % P]);
-      if (ii + 1 < P) w[ii + 1] = unpack_raw<IN16>(raw[ii + 1]);
-      // raw[] is fully consumed at the last rows: request the NEXT tile's samples into it now, before
-      // these rows' FMAs and the FFT the caller runs in emit(), so the DRAM latency hides behind them.
-      if (ii + 2 >= P && i0 + P < sp.count) load_tile(base + (i0 + P) * Ml, raw);
+      if (ii + 1 < P) w[ii + 1] = unpack_raw<IN16>(cur[ii + 1]);
+      // fused kernel: cur[] is fully consumed at the last rows; request the NEXT tile's samples into it
+      // now, before these rows' FMAs and the FFT the caller runs in emit(): the DRAM latency hides there.
+      if (LATE && ii + 2 >= P && i0 + P < sp.count) load_tile(base + (i0 + P) * Ml, cur);
       // Row ii+1 walks the same window slots one tap later (q+1), so each step's two FMAs share their
       // 64-bit window operand (register reuse); its tap order is therefore rotated by one relative to
       // row ii -- pairs are aligned to global row parity (make_span) to keep that deterministic.
@@ -140,15 +144,32 @@ __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, 
       emit((int)ii, i0 + ii, a0);
       if (ii + 1 < P) emit((int)ii + 1, i0 + ii + 1, a1);
     }
+  };
+  if constexpr (EARLY) {
+    // FIR-only kernel: nothing but P rows of FMAs separates two tiles, so the next tile is requested a
+    // whole tile ahead into a second buffer (ping-pong)
+    uint32_t rb[P];
+    for (long long i0 = 0; i0 < sp.count; i0 += 2 * P) {
+      if (i0 + P < sp.count) load_tile(base + (i0 + P) * Ml, rb);
+      rows(i0, raw, std::false_type{});
+      if (i0 + P < sp.count) {
+        if (i0 + 2 * P < sp.count) load_tile(base + (i0 + 2 * P) * Ml, raw);
+        rows(i0 + P, rb, std::false_type{});
+      }
+    }
+  } else {
+    for (long long i0 = 0; i0 < sp.count; i0 += P) rows(i0, raw, std::true_type{});
   }
 }
 
 // Split path, kernel A: FIR only, u rows to global memory (already circularly rotated).
 // grid.x = branch blocks * span blocks; block = 128 threads.
-template <int P, bool IN16>
-__global__ void __launch_bounds__(128) k_fir(ChanParams prm, float2* __restrict__ u) {
-  const int bpb = prm.M < 128 ? prm.M : 128;       // branches per block
-  const int nbb = prm.M / bpb;                     // branch blocks
+// MT = M when instantiated for a fixed channel count (immediate load/store offsets), 0 = any M.
+template <int P, bool IN16, int MT>
+__global__ void __launch_bounds__(128, 4) k_fir(ChanParams prm, float2* __restrict__ u) {
+  const int Mv = MT ? MT : prm.M;
+  const int bpb = Mv < 128 ? Mv : 128;             // branches per block
+  const int nbb = Mv / bpb;                        // branch blocks
   const int groups = 128 / bpb;                    // spans handled side by side in one block
   const int bb = blockIdx.x % nbb, g = threadIdx.x / bpb;
   const int p = bb * bpb + threadIdx.x % bpb;
@@ -157,10 +178,10 @@ __global__ void __launch_bounds__(128) k_fir(ChanParams prm, float2* __restrict_
   for (long long s = (long long)(blockIdx.x / nbb) * groups + g; s < nspans; s += sstride) {
     const Span sp = make_span(prm, s);
     if (sp.count <= 0) continue;
-    const int r = (p - sp.shift + prm.M) % prm.M;   // u'[r] = u[(r + shift) mod M]
-    float2* dst = u + (sp.m0 - prm.row_base) * (long long)prm.M + r;
-    const long long rstride = (long long)prm.os * prm.M;
-    fir_span<P, IN16, 0>(prm, sp, p, [&](int, long long i, float2 v) {
+    const int r = (p - sp.shift + Mv) % Mv;        // u'[r] = u[(r + shift) mod M]
+    float2* dst = u + (sp.m0 - prm.row_base) * (long long)Mv + r;
+    const long long rstride = (long long)prm.os * Mv;
+    fir_span<P, IN16, MT, true>(prm, sp, p, [&](int, long long i, float2 v) {
       if (i >= sp.skip && i < sp.count) dst[i * rstride] = v;
     });
   }
@@ -210,6 +231,56 @@ __global__ void __launch_bounds__(NT) k_fft_rows(const float2* __restrict__ u, f
   }
 }
 
+// Row FFT for the large sizes of the split path (M = 512..4096, first radix 16): ROWS*M = 4096
+// elements per block iteration, 256 threads, exactly one radix-16 butterfly per thread in the first
+// pass.  That pass reads its 16 operands straight from global memory into registers (no staging
+// copy), and the operands of the block's NEXT rows are requested before this iteration's passes run,
+// so DRAM latency overlaps the shared-memory passes.  Twiddles come from the global table through L1.
+// In-place safe (a block only reads and writes its own rows).
+template <int M, int ROWS>
+__global__ void __launch_bounds__(256, 2) k_fft_rows_big(const float2* u, float2* y, const float2* __restrict__ tw_g,
+                                                         long long nrows) {
+  typedef Plan<M> PL;
+  static_assert(PL::np == 3 && PL::r0 == 16 && ROWS * M == 4096, "large-M plan expected");
+  extern __shared__ float2 smem[];
+  constexpr int S = RowStride<M>::value, BPR0 = M / 16;
+  float2* bufA = smem;
+  float2* bufB = bufA + ROWS * S;
+  const int t = threadIdx.x, row = t / BPR0, j = t % BPR0;
+  auto load = [&](long long r0, float2 (&v)[16]) {
+    const bool ok = r0 + row < nrows;
+    const float2* src = u + (r0 + row) * (long long)M + j;
+    #pragma unroll
+    for (int q = 0; q < 16; q++) v[q] = ok ? src[q * BPR0] : make_float2(0.f, 0.f);
+  };
+  const long long step = (long long)gridDim.x * ROWS;
+  float2 cur[16];
+  long long r0 = (long long)blockIdx.x * ROWS;
+  if (r0 < nrows) load(r0, cur);
+  for (; r0 < nrows; r0 += step) {
+    float2 nxt[16];
+    if (r0 + step < nrows) load(r0 + step, nxt);
+    const long long left = nrows - r0;
+    const int vhi = (int)(left < ROWS ? left : ROWS);
+    // pass 1 (radix 16, no twiddles) from registers, Stockham-transposed into bufA
+    dft<16>(cur);
+    {
+      float2* d = bufA + row * S;
+      #pragma unroll
+      for (int q = 0; q < 16; q++) d[padi<M>(j * 16 + q)] = cur[q];
+    }
+    __syncthreads();
+    stockham_pass<M, PL::r1, PL::r0, ROWS, 256, false, false>(bufA, bufB, tw_g, nullptr, t, nullptr, 0, 0, 0);
+    __syncthreads();
+    stockham_pass<M, PL::r2, PL::r0 * PL::r1, ROWS, 256, true, false>(bufB, bufA, tw_g, nullptr, t, y + r0 * (long long)M,
+                                                                      (long long)M, 0, vhi);
+    // no barrier needed here: the next iteration writes bufA (last read before the barrier above) and
+    // only touches bufB after its own first barrier, which every thread reaches after finishing this pass
+    #pragma unroll
+    for (int q = 0; q < 16; q++) cur[q] = nxt[q];
+  }
+}
+
 // ---- fused K1+K2+K3: one global read (raw int samples), one global write (fp32 channels) ----------
 // A block is G groups of M threads; a group walks spans of rows.  Every RT filtered rows (RT divides
 // P) the group runs the M-point FFT on its shared tile and streams the result to global memory.
@@ -248,7 +319,7 @@ __global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 
     if (sp.count <= 0) continue;                      // the whole group takes the same branch
     const int r = padi<M>((p - sp.shift + M) % M);
     float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
-    fir_span<P, IN16, M>(prm, sp, p, [&](int ii, long long i, float2 v) {
+    fir_span<P, IN16, M, false>(prm, sp, p, [&](int ii, long long i, float2 v) {
       buf0[(ii % RT) * S + r] = v;
       if (ii % RT == RT - 1) {
         group_sync<M>(g);

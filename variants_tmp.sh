@@ -1,0 +1,6 @@
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python tools/bench_configs.py --only cfg3,cfg4,cfg5chan,cfg2 --scale 0.25 | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(d['config'], round(d['ms_per_pass'],3), round(d['MS_per_s']), round(d['frac_of_measured_hbm'],3), d['launches_per_pass'])
+"
