@@ -41,6 +41,13 @@ def _peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def _traffic_from_profiles():
     try:
         with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
@@ -61,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -119,6 +126,7 @@ def cpu_baseline(taps, target_seconds=12.0):
     import numpy as np
     from oracle import pyoracle as orc
     from tests import synth
+    orc.lib().orc_set_num_threads(_host_threads())             # torchrun exports OMP_NUM_THREADS=1
     h = taps.astype(np.float64)
     probe_n = M * 32768
     iq, bw = synth.tones_int16_q11(probe_n, M, seed=2)
@@ -147,10 +155,11 @@ def run_reference(args):
     import numpy as np
     from oracle import pyoracle as orc
     from tests import synth
+    orc.lib().orc_set_num_threads(_host_threads())             # torchrun exports OMP_NUM_THREADS=1
     taps = orc.design_prototype(M, TAPS_PER_BAND)
-    n = M * 32768 * 8                                          # 16.8 M samples per step (0.27 s of signal)
+    n = FS                                                     # a 1 s prefix (61.44 M samples) per step
     iq, bw = synth.tones_int16_q11(M * 32768, M, seed=2)
-    big = np.tile(iq, (8, 1))
+    big = np.tile(iq, (n // (M * 32768) + 1, 1))[:n]
     for _ in range(max(1, min(args.warmup, 2))):
         orc.channelize_raw(big, bw, M, taps, OVERSAMPLE)
     steps = max(1, min(args.steps, 10))
@@ -176,7 +185,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--seconds", type=float, default=float(SECONDS), help="recording length per GPU (default: the config's 10 s)")
@@ -305,7 +314,7 @@ def main():
                 "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "channels": M, "taps": ntaps, "oversample": OVERSAMPLE,
-                           "bit_width": BIT_WIDTH, "samples_per_gpu": n_own, "halo_samples": int(halo),
+                           "bit_width": BIT_WIDTH, "samples_per_gpu": n_own, "halo_samples_per_shard": int(ntaps - 1 + (2 * M - (ntaps - 1) % (2 * M)) % (2 * M)) if world > 1 else 0,
                            "parallelism": f"time-sharded x{world}, no collective",
                            "l2": "inputs (2.46 GB) and outputs (4.92 GB) per step exceed the 126 MB L2; no flush needed"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
