@@ -195,6 +195,64 @@ static int launch_fused_dispatch(::chz* h, const ChanParams& prm, cudaStream_t s
   }
 }
 
+// Cluster path (M = 1024, 2048, 4096): returns 1 when there is no instantiation for (M, P).
+template <int M, int P, bool IN16>
+static int launch_cluster(::chz* h, ChanParams prm, cudaStream_t st) {
+  typedef ClusterCfg<M, P> CC;
+  if constexpr (!CC::ok) {
+    return 1;
+  } else {
+    auto kern = k_chan_cluster<M, P, IN16>;
+    static thread_local int nclusters = 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CC::C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = CC::SMEM; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    if (!nclusters) {
+      CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CC::SMEM));
+      cfg.gridDim = dim3((unsigned)(h->sm_count / CC::C * CC::C));
+      int n = 0;
+      CHZ_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      nclusters = n > 0 ? n : 1;
+    }
+    const LaunchPlan lp = plan_spans(h, prm.nrows, P, 1, 1, nclusters);
+    prm.span_rows = lp.span_rows;
+    prm.spans_per_phase = lp.spans_per_phase;
+    const unsigned ncl = lp.grid.x;   // <= nclusters
+    CHZ_CUDA(h->cluster_ring.reserve((size_t)nclusters * 2 * P * M * sizeof(float2)));
+    cfg.gridDim = dim3(ncl * CC::C);
+    float2* ring = (float2*)h->cluster_ring.p;
+    CHZ_CUDA(cudaLaunchKernelEx(&cfg, kern, prm, ring));
+    h->launches++;
+    return CHZ_OK;
+  }
+}
+
+template <bool IN16>
+static int launch_cluster_dispatch(::chz* h, const ChanParams& prm, cudaStream_t st) {
+#define CHZ_CL_P(MV)                                                   \
+  switch (h->P) {                                                      \
+    case 8: return launch_cluster<MV, 8, IN16>(h, prm, st);            \
+    case 16: return launch_cluster<MV, 16, IN16>(h, prm, st);          \
+    default: return 1;                                                 \
+  }
+  switch (h->M) {
+    case 1024: CHZ_CL_P(1024)
+    case 2048: CHZ_CL_P(2048)
+    case 4096: CHZ_CL_P(4096)
+    default: return 1;
+  }
+#undef CHZ_CL_P
+}
+
+static bool cluster_available(const ::chz* h) {
+  if (h->M != 1024 && h->M != 2048 && h->M != 4096) return false;
+  const uint32_t C = h->M / 512;
+  return (h->P == 8 || h->P == 16) && h->P % C == 0;
+}
+
 static bool fused_available(const ::chz* h) {
   return h->M <= 512 && (h->P == 8 || h->P == 12 || h->P == 16);
 }
@@ -225,9 +283,18 @@ static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, 
     prm.taps = h->d_taps[bw]; prm.tw = h->d_tw; prm.out = out_dev;
     prm.row_base = (long long)h->rows_done; prm.nrows = (long long)rows_new;
     prm.M = (int)h->M; prm.D = (int)h->D; prm.os = (int)h->os;
-    bool fused = fused_available(h) && h->force_path != 2;
+    const bool fused = fused_available(h) && h->force_path != 2;
+    // The cluster kernel is opt-in (CHZ_OPT_FORCE_PATH = 3): measured on B200 it is slower than the
+    // split path (cfg4: 27.8 % vs 39.3 % of the HBM roofline; only 120 of 148 SMs host 8-CTA clusters and
+    // each tile serialises FIR -> release fence -> cluster barrier -> L2 reads -> 3 FFT passes).
+    const bool cluster = cluster_available(h) && h->force_path == 3;
+    if (h->force_path == 3 && !cluster) return CHZ_EINVAL;
     if (h->force_path == 1 && !fused) return CHZ_EINVAL;
-    if (fused) {
+    if (cluster) {
+      rc = in16 ? launch_cluster_dispatch<true>(h, prm, st) : launch_cluster_dispatch<false>(h, prm, st);
+      if (rc == 1) return CHZ_EINVAL;
+      if (rc) return rc;
+    } else if (fused) {
       rc = in16 ? launch_fused_dispatch<true>(h, prm, st) : launch_fused_dispatch<false>(h, prm, st);
       if (rc == 1) return CHZ_EINVAL;
       if (rc) return rc;
@@ -432,6 +499,7 @@ void chz_destroy(chz_t* h) {
   }
   if (h->d_store) cudaFree(h->d_store);
   if (h->d_u) cudaFree(h->d_u);
+  h->cluster_ring.release();
   for (chzi::Scratch* sc : {&h->pdw_hist, &h->pdw_sel, &h->pdw_thr, &h->pdw_cnt, &h->pdw_ev, &h->pdw_pin, &h->pdw_pout}) sc->release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -461,7 +529,7 @@ int chz_set_option(chz_t* h, int opt, int64_t value) {
   switch (opt) {
     case CHZ_OPT_RETAIN: h->retain = value != 0; return CHZ_OK;
     case CHZ_OPT_CHUNK_ROWS: if (value < 0) return CHZ_EINVAL; h->chunk_rows = value; return CHZ_OK;
-    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 2) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
+    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 3) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
     default: return CHZ_EINVAL;
   }
 }

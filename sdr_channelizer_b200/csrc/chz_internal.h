@@ -64,6 +64,9 @@ struct chz {
   float2* d_store = nullptr;
   uint64_t store_rows = 0, store_cap = 0;
 
+  // cluster path: per-cluster L2-resident tile ring
+  chzi::Scratch cluster_ring;
+
   // split-path scratch (FIR output rows)
   float2* d_u = nullptr;
   uint64_t u_cap_rows = 0;

@@ -335,4 +335,85 @@ __global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 
   }
 }
 
+// ---- large M (1024..4096): one fused launch per call on thread-block clusters ----------------------
+// A branch's register window times M threads does not fit one SM, so M/512 CTAs (2, 4 or 8) form a
+// cluster: CTA `rank` owns the 512 contiguous branches [512 rank, 512 rank + 512) for the FIR (same
+// register-window code, coalesced 2 KB loads).  Each tile of P rows goes to a per-cluster scratch ring
+// (2 tiles x P x M float2, <= 1 MB, rewritten continuously so it lives in L2 and never reaches DRAM);
+// after ONE cluster barrier per tile every CTA transforms P/C whole rows of that tile (first radix-16
+// pass straight from the scratch into registers, two more passes in shared memory) and streams them
+// to the output.  The ring is double buffered: tile t+2 reuses tile t's slot only after barrier t+1,
+// which every CTA reaches after finishing its FFT of tile t.
+// DRAM traffic is the fused kernel's (raw in once, fp32 out once); the intermediate costs L2 bandwidth.
+template <int M, int P> struct ClusterCfg {
+  static constexpr int C = M / 512;                  // CTAs per cluster
+  static constexpr int RPC = P / C;                  // rows each CTA transforms per tile
+  static constexpr bool ok = (M == 1024 || M == 2048 || M == 4096) && (P % C == 0) && RPC >= 1;
+  // two FFT tile buffers + the inter-pass twiddle table (the cluster barrier invalidates L1 every tile,
+  // so twiddles read through L1 would come from L2 again each time)
+  static constexpr size_t SMEM = ((size_t)2 * (RPC > 0 ? RPC : 1) * RowStride<M>::value + M) * sizeof(float2);
+};
+
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int M, int P, bool IN16>
+__global__ void __launch_bounds__(512, 1) k_chan_cluster(ChanParams prm, float2* __restrict__ scratch) {
+  typedef ClusterCfg<M, P> CC;
+  typedef Plan<M> PL;
+  static_assert(PL::np == 3 && PL::r0 == 16, "large-M plan expected");
+  constexpr int C = CC::C, RPC = CC::RPC, S = RowStride<M>::value, BPR0 = M / 16;
+  extern __shared__ float2 smem[];
+  float2* bufA = smem;
+  float2* bufB = bufA + RPC * S;
+  float2* tw = bufB + RPC * S;
+  const int t = threadIdx.x;
+  for (int i = t; i < M; i += 512) tw[i] = prm.tw[i];
+  __syncthreads();
+  const int rank = (int)cluster_ctarank();
+  const long long cid = blockIdx.x / C, ncl = gridDim.x / C;
+  const int p = rank * 512 + t;
+  float2* ring = scratch + (size_t)cid * 2 * P * M;
+  const long long nspans = prm.spans_per_phase * prm.os;
+  const long long rstride = (long long)prm.os * M;
+  const int frow = t / BPR0, fj = t % BPR0;            // this thread's first-pass butterfly: (row, column)
+  unsigned tile = 0;
+  for (long long s = cid; s < nspans; s += ncl) {      // cluster-uniform loop
+    const Span sp = make_span(prm, s);
+    if (sp.count <= 0) continue;
+    const int r = (p - sp.shift + M) % M;              // circular shift of the oversampled odd rows
+    float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
+    fir_span<P, IN16, M, false>(prm, sp, p, [&](int ii, long long i, float2 v) {
+      float2* slot = ring + (size_t)(tile & 1) * P * M;
+      slot[(size_t)ii * M + r] = v;
+      if (ii == P - 1) {
+        cluster_barrier();                             // the whole tile is in the ring (L2)
+        const long long i0 = i - (P - 1) + rank * RPC; // first span row this CTA transforms
+        const long long left = sp.count - i0;
+        const int vhi = (int)(left < RPC ? (left < 0 ? 0 : left) : RPC);
+        const int vlo = i0 < sp.skip ? (int)(sp.skip - i0) : 0;
+        // pass 1 (radix 16) from the ring, bypassing L1 (another SM wrote it)
+        float2 x[16];
+        const float2* src = slot + (size_t)(rank * RPC + frow) * M + fj;
+        #pragma unroll
+        for (int q = 0; q < 16; q++) x[q] = __ldcg(src + q * BPR0);
+        dft<16>(x);
+        {
+          float2* d = bufA + frow * S;
+          #pragma unroll
+          for (int q = 0; q < 16; q++) d[padi<M>(fj * 16 + q)] = x[q];
+        }
+        __syncthreads();
+        stockham_pass<M, PL::r1, PL::r0, RPC, 512, false, false>(bufA, bufB, tw, nullptr, t, nullptr, 0, 0, 0);
+        __syncthreads();
+        stockham_pass<M, PL::r2, PL::r0 * PL::r1, RPC, 512, true, false>(bufB, bufA, tw, nullptr, t,
+                                                                         gout + i0 * rstride, rstride, vlo, vhi);
+        tile++;
+      }
+    });
+  }
+}
+
 }  // namespace chzi

@@ -104,7 +104,8 @@ def test_channelizer_matches_oracle(orc, M, P, os_, kind, n):
 
 @pytest.mark.parametrize("M,P,os_,path", [(64, 16, 1, 1), (64, 16, 2, 1), (64, 12, 1, 1), (8, 8, 1, 1), (256, 16, 1, 1),
                                           (512, 8, 2, 1), (32, 12, 2, 1), (128, 16, 1, 1), (16, 16, 1, 1),
-                                          (64, 16, 1, 2), (1024, 16, 2, 0), (4096, 8, 1, 0), (64, 24, 1, 0), (64, 32, 2, 0)])
+                                          (64, 16, 1, 2), (1024, 16, 2, 0), (4096, 8, 1, 0), (64, 24, 1, 0), (64, 32, 2, 0),
+                                          (4096, 16, 1, 3), (2048, 16, 2, 3), (1024, 8, 1, 3)])
 def test_random_taps_every_tap_index_matters(orc, M, P, os_, path):
     """A designed prototype has tiny end taps, which would hide a mis-indexed tap or window slot
     below the 1e-5 tolerance; with random taps of equal weight any such slip is an O(1/P) error."""
@@ -211,6 +212,28 @@ def test_impulse_and_tone_known_answers():
     iq = np.stack([np.rint(x.real * 32768), np.rint(x.imag * 32768)], axis=1).astype(np.int16)
     y = ch(iq, 16)
     assert abs(abs(y[-1, k0]) - 0.5) < 1e-4 and np.max(np.abs(np.delete(y[-1], k0))) < 1e-3
+    ch.close()
+
+
+@pytest.mark.parametrize("M,P,os_,bw", [(64, 16, 1, 12), (8, 8, 2, 8), (1024, 16, 2, 16), (64, 32, 1, 10), (256, 12, 1, 5)])
+def test_edge_lengths_ragged_and_tiny(orc, M, P, os_, bw):
+    """Empty, shorter than a frame, exactly one frame, one sample more, shorter than the prototype,
+    ragged tails (the reference trims to a multiple of M, create_pdws_channelized.m:52-54)."""
+    _torch()
+    D, L = M // os_, M * P
+    rng = np.random.default_rng(M + bw)
+    taps = pkg.design_prototype(M, P)
+    ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=os_)
+    lim = 2 ** (bw - 1)
+    dt = np.int8 if bw <= 8 else np.int16
+    for n in (0, 1, D - 1, D, D + 1, M, 2 * M + 3, L - 1, L, L + D + 1, 3 * L + 5):
+        iq = rng.integers(-lim, lim, size=(n, 2)).astype(dt)
+        ch.reset()
+        y = ch(iq, bw)
+        ref = orc.channelize_raw(iq, bw, M, taps.astype(np.float64), os_)
+        assert y.shape == ref.shape == (n // D, M), n
+        if y.size:
+            assert synth.rel_rms(y, ref) <= TOL, n
     ch.close()
 
 

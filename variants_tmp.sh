@@ -1,5 +1,5 @@
-for mb in 100000 96 64 48 32; do echo "chunk MB $mb"; CHZ_SPLIT_CHUNK_MB=$mb python tools/bench_configs.py --only cfg3,cfg4 --scale 0.25 | python -c "
+python tools/bench_configs.py --only cfg3,cfg4 --scale 0.25 | python -c "
 import sys,json
 for l in sys.stdin:
-    d=json.loads(l); print(d['config'], round(d['ms_per_pass'],3), round(d['MS_per_s']), round(d['frac_of_measured_hbm'],3), d['launches_per_pass'])
-"; done
+    d=json.loads(l); print(d.get('config'), d.get('error') or (round(d['ms_per_pass'],3), round(d['MS_per_s']), round(d['frac_of_measured_hbm'],3), d['launches_per_pass']))
+"
