@@ -222,6 +222,8 @@ def main():
     y = torch.empty((rows_total, M), dtype=torch.complex64, device=dev)
     taps = pkg.design_prototype(M, TAPS_PER_BAND)
     ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=OVERSAMPLE)
+    if os.environ.get("CHZ_BENCH_PATH"):                          # kernel A/B experiments only
+        ch.set_option(pkg.CHZ_OPT_FORCE_PATH, int(os.environ["CHZ_BENCH_PATH"]))
     torch.cuda.synchronize()
     stream = torch.cuda.Stream(device=dev)        # the kernels AND the timing events live on this stream
     torch.cuda.set_stream(stream)

@@ -195,6 +195,37 @@ static int launch_fused_dispatch(::chz* h, const ChanParams& prm, cudaStream_t s
   }
 }
 
+// Warp-specialised fused kernel (M = 64).
+template <int P, bool IN16>
+static int launch_ws(::chz* h, ChanParams prm, cudaStream_t st) {
+  typedef WsCfg<64, P> WC;
+  auto kern = k_chan_ws<64, P, IN16>;
+  static thread_local int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WC::SMEM));
+    int nb = 0;
+    CHZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, WC::SMEM));
+    blocks_per_sm = nb > 0 ? nb : 1;
+  }
+  const LaunchPlan lp = plan_spans(h, prm.nrows, P, 2, blocks_per_sm);
+  prm.span_rows = lp.span_rows;
+  prm.spans_per_phase = lp.spans_per_phase;
+  kern<<<lp.grid, 256, WC::SMEM, st>>>(prm);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  return CHZ_OK;
+}
+template <bool IN16>
+static int launch_ws_dispatch(::chz* h, const ChanParams& prm, cudaStream_t st) {
+  switch (h->P) {
+    case 8: return launch_ws<8, IN16>(h, prm, st);
+    case 12: return launch_ws<12, IN16>(h, prm, st);
+    case 16: return launch_ws<16, IN16>(h, prm, st);
+    default: return 1;
+  }
+}
+static bool ws_available(const ::chz* h) { return h->M == 64 && (h->P == 8 || h->P == 12 || h->P == 16); }
+
 // Cluster path (M = 1024, 2048, 4096): returns 1 when there is no instantiation for (M, P).
 template <int M, int P, bool IN16>
 static int launch_cluster(::chz* h, ChanParams prm, cudaStream_t st) {
@@ -289,8 +320,13 @@ static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, 
     // each tile serialises FIR -> release fence -> cluster barrier -> L2 reads -> 3 FFT passes).
     const bool cluster = cluster_available(h) && h->force_path == 3;
     if (h->force_path == 3 && !cluster) return CHZ_EINVAL;
+    const bool ws = ws_available(h) && h->force_path == 4;
+    if (h->force_path == 4 && !ws) return CHZ_EINVAL;
     if (h->force_path == 1 && !fused) return CHZ_EINVAL;
-    if (cluster) {
+    if (ws) {
+      rc = in16 ? launch_ws_dispatch<true>(h, prm, st) : launch_ws_dispatch<false>(h, prm, st);
+      if (rc) return rc == 1 ? CHZ_EINVAL : rc;
+    } else     if (cluster) {
       rc = in16 ? launch_cluster_dispatch<true>(h, prm, st) : launch_cluster_dispatch<false>(h, prm, st);
       if (rc == 1) return CHZ_EINVAL;
       if (rc) return rc;
@@ -529,7 +565,7 @@ int chz_set_option(chz_t* h, int opt, int64_t value) {
   switch (opt) {
     case CHZ_OPT_RETAIN: h->retain = value != 0; return CHZ_OK;
     case CHZ_OPT_CHUNK_ROWS: if (value < 0) return CHZ_EINVAL; h->chunk_rows = value; return CHZ_OK;
-    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 3) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
+    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 4) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
     default: return CHZ_EINVAL;
   }
 }

@@ -2,6 +2,9 @@
 // Reference math replaced: matlab/create_pdws_channelized.m:35-38 (normalise) and :57
 // (iq = channelizer(iq), MathWorks dsp.Channelizer — closed source; definition in DESIGN.md).
 #pragma once
+#ifndef CHZ_FUSED_MINB
+#define CHZ_FUSED_MINB 2
+#endif
 #include <type_traits>
 
 #include "chz_device.cuh"
@@ -84,7 +87,9 @@ __device__ __forceinline__ Span make_span(const ChanParams& p, long long sp) {
 // registers; a new row costs one 4-byte (int16) or 2-byte (int8) coalesced load and P packed FMAs
 // (fma.rn.f32x2 on (re,im) with the tap duplicated).  `emit(i, value)` receives row i of the span.
 // MT: number of channels when known at compile time (fused kernel), 0 = take prm.M.
-template <int P, bool IN16, int MT, bool EARLY, typename Emit>
+// PF: prefetch policy for the next tile's raw samples: 0 = late (at the last rows; the fused kernel's FFT hides
+// the latency), 1 = a whole tile ahead into a second buffer (FIR-only kernel), 2 = half a tile ahead, in place.
+template <int P, bool IN16, int MT, int PF, typename Emit>
 __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, int p, Emit emit) {
   typedef typename RawT<IN16>::type raw_t;
   const long long Ml = MT ? MT : prm.M;
@@ -97,15 +102,19 @@ __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, 
   const raw_t* __restrict__ inp = (const raw_t*)prm.in - prm.in_base;   // inp[idx] for idx in [in_base, in_end)
   // P raw words at lo, lo+M, ...: unconditional coalesced loads when the whole tile lies inside this
   // call's input (every tile but the first/last few of a call), guarded loads otherwise.
-  auto load_tile = [&](long long lo, uint32_t (&raw)[P]) {
-    if (lo >= prm.in_base && lo + (P - 1) * Ml < in_end) {
+  auto load_part = [&](long long lo, uint32_t (&raw)[P], auto first, auto count) {   // raw[first + k] = x[lo + (first + k) M]
+    constexpr int F = decltype(first)::value, N = decltype(count)::value;
+    if (lo + F * Ml >= prm.in_base && lo + (F + N - 1) * Ml < in_end) {
       const raw_t* __restrict__ src = inp + lo;
       #pragma unroll
-      for (int ii = 0; ii < P; ii++) raw[ii] = __ldg(src + ii * Ml);
+      for (int ii = F; ii < F + N; ii++) raw[ii] = __ldg(src + ii * Ml);
     } else {
       #pragma unroll
-      for (int ii = 0; ii < P; ii++) raw[ii] = load_raw<IN16>(prm, lo + ii * Ml);
+      for (int ii = F; ii < F + N; ii++) raw[ii] = load_raw<IN16>(prm, lo + ii * Ml);
     }
+  };
+  auto load_tile = [&](long long lo, uint32_t (&raw)[P]) {
+    load_part(lo, raw, std::integral_constant<int, 0>{}, std::integral_constant<int, P>{});
   };
   // warm-up rows -P..-1 and tile 0 are requested back to back so their latencies overlap
   uint32_t raw[P];
@@ -132,6 +141,10 @@ __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, 
       // fused kernel: cur[] is fully consumed at the last rows; request the NEXT tile's samples into it
       // now, before these rows' FMAs and the FFT the caller runs in emit(): the DRAM latency hides there.
       if (LATE && ii + 2 >= P && i0 + P < sp.count) load_tile(base + (i0 + P) * Ml, cur);
+      if (PF == 2 && i0 + P < sp.count) {   // HALF: refill each half of cur[] as soon as it has been consumed
+        if (ii + 2 == P / 2) load_part(base + (i0 + P) * Ml, cur, std::integral_constant<int, 0>{}, std::integral_constant<int, P / 2>{});
+        if (ii + 2 >= P) load_part(base + (i0 + P) * Ml, cur, std::integral_constant<int, P / 2>{}, std::integral_constant<int, P - P / 2>{});
+      }
       // Row ii+1 walks the same window slots one tap later (q+1), so each step's two FMAs share their
       // 64-bit window operand (register reuse); its tap order is therefore rotated by one relative to
       // row ii -- pairs are aligned to global row parity (make_span) to keep that deterministic.
@@ -145,7 +158,7 @@ __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, 
       if (ii + 1 < P) emit((int)ii + 1, i0 + ii + 1, a1);
     }
   };
-  if constexpr (EARLY) {
+  if constexpr (PF == 1) {
     // FIR-only kernel: nothing but P rows of FMAs separates two tiles, so the next tile is requested a
     // whole tile ahead into a second buffer (ping-pong)
     uint32_t rb[P];
@@ -157,6 +170,8 @@ __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, 
         rows(i0 + P, rb, std::false_type{});
       }
     }
+  } else if constexpr (PF == 2) {
+    for (long long i0 = 0; i0 < sp.count; i0 += P) rows(i0, raw, std::false_type{});
   } else {
     for (long long i0 = 0; i0 < sp.count; i0 += P) rows(i0, raw, std::true_type{});
   }
@@ -181,7 +196,7 @@ __global__ void __launch_bounds__(128, 4) k_fir(ChanParams prm, float2* __restri
     const int r = (p - sp.shift + Mv) % Mv;        // u'[r] = u[(r + shift) mod M]
     float2* dst = u + (sp.m0 - prm.row_base) * (long long)Mv + r;
     const long long rstride = (long long)prm.os * Mv;
-    fir_span<P, IN16, MT, true>(prm, sp, p, [&](int, long long i, float2 v) {
+    fir_span<P, IN16, MT, 1>(prm, sp, p, [&](int, long long i, float2 v) {
       if (i >= sp.skip && i < sp.count) dst[i * rstride] = v;
     });
   }
@@ -299,7 +314,7 @@ template <int M> __device__ __forceinline__ void group_sync(int g) {
 }
 
 template <int M, int P, bool IN16>
-__global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 ? 2 : 1) k_chan_fused(ChanParams prm) {
+__global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 ? CHZ_FUSED_MINB : 1) k_chan_fused(ChanParams prm) {
   extern __shared__ float2 smem[];
   typedef FusedCfg<M, P> CF;
   constexpr int NT = CF::NT, G = CF::G, RT = CF::RT, S = RowStride<M>::value;
@@ -319,7 +334,7 @@ __global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 
     if (sp.count <= 0) continue;                      // the whole group takes the same branch
     const int r = padi<M>((p - sp.shift + M) % M);
     float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
-    fir_span<P, IN16, M, false>(prm, sp, p, [&](int ii, long long i, float2 v) {
+    fir_span<P, IN16, M, 0>(prm, sp, p, [&](int ii, long long i, float2 v) {
       buf0[(ii % RT) * S + r] = v;
       if (ii % RT == RT - 1) {
         group_sync<M>(g);
@@ -332,6 +347,103 @@ __global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 
         if (Plan<M>::np != 2) group_sync<M>(g);   // the last pass of 1- and 3-pass plans reads buf0
       }
     });
+  }
+}
+
+// ---- warp-specialised fused kernel (M = 64): FIR warps and FFT warps ------------------------------
+// The plain fused kernel alternates two phases in every warp: the FIR (FMA-pipe bound) and the FFT
+// (shared-memory / latency bound), with only 16 warps per SM because every thread carries the FIR
+// state AND the FFT registers.  Here a block is two warpgroups: warps 0-3 run the FIR of two groups
+// (64 branches each) and nothing else, warps 4-7 run the FFT of those two groups.  The FIR warpgroup
+// raises its register budget (setmaxnreg.inc), the FFT warpgroup lowers it (setmaxnreg.dec), so three
+// blocks (24 warps) fit an SM and the two kinds of work overlap instead of alternating.
+// Hand-off: per group a ring of WS_NB tile buffers in shared memory guarded by mbarriers
+// (full[b]: 64 FIR threads arrive after writing a tile; empty[b]: 64 FFT threads arrive after their
+// first pass has consumed it).
+constexpr int WS_NB = 2;
+constexpr int WS_FIR_REGS = 104, WS_FFT_REGS = 56;
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+template <int M, int P> struct WsCfg {
+  static constexpr int S = RowStride<M>::value;
+  static constexpr int TILE = P * S;                                   // float2 per tile buffer
+  // per group: WS_NB ring buffers + one FFT scratch buffer; per block: 2 groups + twiddles + barriers
+  static constexpr size_t SMEM = (size_t)(2 * (WS_NB + 1) * TILE + M) * sizeof(float2) + 2 * 2 * WS_NB * sizeof(uint64_t);
+};
+
+template <int M, int P, bool IN16>
+__global__ void __launch_bounds__(256, 3) k_chan_ws(ChanParams prm) {
+  static_assert(M == 64, "two warps per group");
+  typedef WsCfg<M, P> WC;
+  constexpr int S = WC::S;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tw = (float2*)smem_raw;                                      // M twiddles
+  float2* bufs = tw + M;                                               // [2 groups][WS_NB + 1][P][S]
+  uint64_t* bars = (uint64_t*)(bufs + 2 * (WS_NB + 1) * WC::TILE);     // [2 groups][full WS_NB | empty WS_NB]
+  const int warp = threadIdx.x >> 5;
+  const bool is_fir = warp < 4;
+  const int g = (warp & 3) >> 1;                                       // group inside the block
+  const int p = threadIdx.x & 63;                                      // branch (FIR) / FFT thread index in the group
+  float2* ring = bufs + (size_t)g * (WS_NB + 1) * WC::TILE;
+  float2* scratch = ring + WS_NB * WC::TILE;
+  uint64_t* full = bars + g * 2 * WS_NB;
+  uint64_t* empty = full + WS_NB;
+  for (int i = threadIdx.x; i < M; i += 256) tw[i] = prm.tw[i];
+  if (threadIdx.x < 2 * 2 * WS_NB) mbar_init(bars + threadIdx.x, 64);
+  __syncthreads();
+  const long long nspans = prm.spans_per_phase * prm.os;
+  const long long rstride = (long long)prm.os * M;
+  const long long gg = (long long)blockIdx.x * 2 + g, gstride = (long long)gridDim.x * 2;
+  unsigned tile = 0;                                                   // tiles handled so far by this group
+  if (is_fir) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_FIR_REGS));
+    for (long long s = gg; s < nspans; s += gstride) {
+      const Span sp = make_span(prm, s);
+      if (sp.count <= 0) continue;
+      const int r = padi<M>((p - sp.shift + M) % M);
+      fir_span<P, IN16, M, 2>(prm, sp, p, [&](int ii, long long, float2 v) {
+        const unsigned b = tile % WS_NB, n = tile / WS_NB;
+        if (ii == 0 && n > 0) mbar_wait(&empty[b], (n - 1) & 1);       // the FFT warps are done with this buffer
+        ring[b * WC::TILE + ii * S + r] = v;
+        if (ii == P - 1) { mbar_arrive(&full[b]); tile++; }
+      });
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_FFT_REGS));
+    for (long long s = gg; s < nspans; s += gstride) {
+      const Span sp = make_span(prm, s);
+      if (sp.count <= 0) continue;
+      float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
+      for (long long i0 = 0; i0 < sp.count; i0 += P) {
+        const unsigned b = tile % WS_NB, n = tile / WS_NB;
+        const long long left = sp.count - i0;
+        const int vhi = (int)(left < P ? left : P);
+        const int vlo = i0 < sp.skip ? (int)(sp.skip - i0) : 0;
+        mbar_wait(&full[b], n & 1);
+        stockham_pass<M, Plan<M>::r0, 1, P, 64, false, false>(ring + b * WC::TILE, scratch, tw, nullptr, p, nullptr, 0, 0, 0);
+        mbar_arrive(&empty[b]);                                        // ring buffer b may be refilled
+        asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");
+        stockham_pass<M, Plan<M>::r1, Plan<M>::r0, P, 64, true, false>(scratch, nullptr, tw, nullptr, p, gout + i0 * rstride,
+                                                                      rstride, vlo, vhi);
+        asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");       // scratch is free for the next tile
+        tile++;
+      }
+    }
   }
 }
 
@@ -385,7 +497,7 @@ __global__ void __launch_bounds__(512, 1) k_chan_cluster(ChanParams prm, float2*
     if (sp.count <= 0) continue;
     const int r = (p - sp.shift + M) % M;              // circular shift of the oversampled odd rows
     float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
-    fir_span<P, IN16, M, false>(prm, sp, p, [&](int ii, long long i, float2 v) {
+    fir_span<P, IN16, M, 0>(prm, sp, p, [&](int ii, long long i, float2 v) {
       float2* slot = ring + (size_t)(tile & 1) * P * M;
       slot[(size_t)ii * M + r] = v;
       if (ii == P - 1) {
