@@ -92,8 +92,10 @@ int chz_design_prototype(uint32_t M, uint32_t taps_per_band, double stopband_att
 typedef struct chz chz_t;
 typedef struct chz_cf32 { float re, im; } chz_cf32;
 
-/* M: power of two in [8, 4096]; ntaps: positive multiple of M, ntaps/M <= 32; oversample 1
- * (D = M, critically sampled) or 2 (D = M/2).  taps == NULL -> default prototype (12*M taps, 80 dB;
+/* M: 2..4096.  Powers of two >= 8 run the tuned kernels; any other M (the reference's natural
+ * M = fs*1e-6 = 56, create_pdws_channelized.m:31) runs a functional direct-FIR + O(M^2) DFT path.
+ * ntaps: positive multiple of M, ntaps/M <= 32; oversample 1 (D = M, critically sampled) or 2
+ * (D = M/2, M even).  taps == NULL -> default prototype (12*M taps, 80 dB;
  * ntaps is then ignored).  Taps are copied. */
 int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversample, chz_t** out);
 void chz_destroy(chz_t* h);

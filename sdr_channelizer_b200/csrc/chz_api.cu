@@ -135,6 +135,20 @@ static int launch_fft_rows_big(::chz* h, const float2* u, float2* y, long long n
 }
 
 static int launch_fft_rows(::chz* h, const float2* u, float2* y, long long nrows, cudaStream_t st) {
+  if (h->generic) {
+    if (nrows < 1) return CHZ_OK;
+    const size_t smem = (size_t)2 * h->M * sizeof(float2);
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+      CHZ_CUDA(cudaFuncSetAttribute(k_dft_rows_any, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * (int)sizeof(float2)));
+      attr_set = true;
+    }
+    long long blocks = nrows < (long long)h->sm_count * 8 ? nrows : (long long)h->sm_count * 8;
+    k_dft_rows_any<<<(unsigned)blocks, 256, smem, st>>>(u, y, h->d_tw, (int)h->M, nrows);
+    h->launches++;
+    CHZ_CUDA(cudaGetLastError());
+    return CHZ_OK;
+  }
   switch (h->M) {
     case 8: return launch_fft_rows_t<8, 256, 256>(h, u, y, nrows, st);
     case 16: return launch_fft_rows_t<16, 128, 256>(h, u, y, nrows, st);
@@ -152,7 +166,7 @@ static int launch_fft_rows(::chz* h, const float2* u, float2* y, long long nrows
 
 template <bool IN16>
 static int launch_fir_dispatch(::chz* h, const ChanParams& prm, float2* u, cudaStream_t st) {
-  switch (h->P) {
+  switch (h->generic ? 0u : h->P) {
     case 4: return launch_fir<4, IN16>(h, prm, u, st);
     case 8: return launch_fir<8, IN16>(h, prm, u, st);
     case 12: return launch_fir<12, IN16>(h, prm, u, st);
@@ -285,7 +299,7 @@ static bool cluster_available(const ::chz* h) {
 }
 
 static bool fused_available(const ::chz* h) {
-  return h->M <= 512 && (h->P == 8 || h->P == 12 || h->P == 16);
+  return !h->generic && h->M >= 8 && h->M <= 512 && (h->P == 8 || h->P == 12 || h->P == 16);
 }
 
 static int ensure_taps(::chz* h, uint32_t bw) {
@@ -444,8 +458,9 @@ int chz_abi_version(void) { return CHZ_ABI_VERSION; }
 int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversample, chz_t** out) {
   if (!out) return CHZ_EINVAL;
   *out = nullptr;
-  if (M < 8 || M > 4096 || (M & (M - 1))) return CHZ_EINVAL;
+  if (M < 2 || M > 4096) return CHZ_EINVAL;
   if (oversample != 1 && oversample != 2) return CHZ_EINVAL;
+  if (M % oversample != 0) return CHZ_EINVAL;
   if (taps && (ntaps == 0 || ntaps % M != 0 || ntaps / M > 32)) return CHZ_EINVAL;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return CHZ_ENODEVICE; }
@@ -459,6 +474,7 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
   h->device = dev;
   h->sm_count = prop.multiProcessorCount;
   h->M = M; h->os = oversample; h->D = M / oversample;
+  h->generic = M < 8 || (M & (M - 1)) != 0;   // no radix plan: direct FIR + O(M^2) row DFT kernels
   if (taps) {
     h->taps.assign(taps, taps + ntaps);
   } else {
@@ -481,7 +497,12 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
   // Inter-pass twiddles of the Stockham plan (same radices as Plan<M> on the device), laid out per pass
   // as entry (q-1)*NS + k = W_{NS R}^{q k} = e^{+j 2 pi q k / (NS R)} so a warp reads consecutive k.
   std::vector<float2> tw(M, make_float2(1.f, 0.f));
-  {
+  if (h->generic) {   // plain table W_M^i = e^{+j 2 pi i / M}
+    for (uint32_t i = 0; i < M; i++) {
+      const double a = 2.0 * 3.14159265358979323846264338327950288 * (double)i / (double)M;
+      tw[i] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+  } else {
     int r[3] = {1, 1, 1};
     switch (M) {
       case 8: r[0] = 8; break;              case 16: r[0] = 16; break;

@@ -45,6 +45,7 @@ struct chz {
   int device = 0;
   int sm_count = 148;
   uint32_t M = 0, P = 0, L = 0, os = 1, D = 0;
+  bool generic = false;                 // M is not a power of two >= 8: direct FIR + O(M^2) DFT kernels
   std::vector<float> taps;              // prototype as given (unscaled), h[qM + p]
   float* d_taps[17] = {nullptr};        // per bit width: taps * 2^-(bw-1), uploaded on first use
   float2* d_tw = nullptr;               // e^{+j 2 pi i / M}

@@ -222,6 +222,34 @@ __global__ void k_fir_any(ChanParams prm, int P, float2* __restrict__ u) {
   }
 }
 
+// Any-M row DFT (the reference's natural channel counts are not powers of two: M = fs*1e-6 = 56,
+// matlab/create_pdws_channelized.m:31).  Direct evaluation y_k = sum_p u_p W_M^{kp}, O(M^2) per row,
+// table W_M^i in shared memory indexed by (k p) mod M.  Functional path, not tuned.
+__global__ void __launch_bounds__(256) k_dft_rows_any(const float2* u, float2* y, const float2* __restrict__ tw_g, int M,
+                                                      long long nrows) {
+  extern __shared__ float2 smem[];
+  float2* row = smem;
+  float2* tw = smem + M;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) tw[i] = tw_g[i];
+  for (long long r = blockIdx.x; r < nrows; r += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < M; i += blockDim.x) row[i] = u[r * M + i];
+    __syncthreads();
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+      float2 acc = make_float2(0.f, 0.f);
+      int idx = 0;
+      for (int p = 0; p < M; p++) {
+        const float2 a = row[p], w = tw[idx];
+        acc.x = fmaf(a.x, w.x, fmaf(-a.y, w.y, acc.x));
+        acc.y = fmaf(a.x, w.y, fmaf(a.y, w.x, acc.y));
+        idx += k;
+        if (idx >= M) idx -= M;
+      }
+      y[r * M + k] = acc;
+    }
+  }
+}
+
 // Split path, kernel B (also K3 on its own): M-point FFT of rows in global memory.
 // One block transforms ROWS rows at a time.  Dynamic smem: 2 * ROWS * RowStride<M> float2 + M float2.
 template <int M, int ROWS, int NT>

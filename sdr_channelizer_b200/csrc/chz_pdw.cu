@@ -44,17 +44,18 @@ __global__ void __launch_bounds__(256) k_hist(const float2* __restrict__ y, long
   __shared__ uint32_t sh[4 * kBins];
   for (int i = threadIdx.x; i < 4 * kBins; i += 256) sh[i] = 0;
   const int cl = threadIdx.x & 3, ch = blockIdx.x * 4 + cl;
+  const bool ch_ok = ch < M;                       // M need not be a multiple of 4
   const int shift = pass_shift(pass);
   const uint32_t bmask = pass_mask(pass), pmask = prefix_mask(pass);
   uint32_t p0 = 0, p1 = 0;
-  if (pass > 0) { p0 = st[ch].prefix[0]; p1 = st[ch].prefix[1]; }
+  if (pass > 0 && ch_ok) { p0 = st[ch].prefix[0]; p1 = st[ch].prefix[1]; }
   const bool split = p0 != p1;
   __syncthreads();
   const long long rows_per_block = (nrows + gridDim.y - 1) / gridDim.y;
   const long long r_begin = (long long)blockIdx.y * rows_per_block;
   long long r_end = r_begin + rows_per_block;
   if (r_end > nrows) r_end = nrows;
-  for (long long r = r_begin + (threadIdx.x >> 2); r < r_end; r += 64) {
+  for (long long r = r_begin + (threadIdx.x >> 2); ch_ok && r < r_end; r += 64) {
     const uint32_t bits = __float_as_uint(mag_of(y[r * M + ch]));
     const uint32_t pre = bits & pmask, bin = (bits >> shift) & bmask;
     if (pre == p0) atomicAdd(&sh[cl * kBins + bin], 1u);
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256) k_hist(const float2* __restrict__ y, long
   __syncthreads();
   for (int i = threadIdx.x; i < 4 * kBins; i += 256) {
     const uint32_t v = sh[i];
-    if (v) atomicAdd(&hist[((size_t)(blockIdx.x * 4 + i / kBins) * 2) * kBins + (i % kBins)], v);
+    if (v && blockIdx.x * 4 + i / kBins < M) atomicAdd(&hist[((size_t)(blockIdx.x * 4 + i / kBins) * 2) * kBins + (i % kBins)], v);
   }
 }
 
@@ -125,15 +126,17 @@ __global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, lo
   const long long total_warps = nchunks / streams + (nchunks % streams ? 1 : 0);
   const long long wchunk = warp_id / ch_groups;
   if (wchunk >= total_warps) return;                      // warp-uniform
-  const int ch = (int)(warp_id % ch_groups) * 32 + (lane % lanes_ch);
+  const int ch_raw = (int)(warp_id % ch_groups) * 32 + (lane % lanes_ch);
   const long long chunk = wchunk * streams + lane / lanes_ch;
-  const bool live = chunk < nchunks;
+  // lanes beyond M (M not a multiple of 32) or beyond streams*lanes_ch idle but still vote in the ballots
+  const bool live = chunk < nchunks && ch_raw < M && lane < streams * lanes_ch;
+  const int ch = ch_raw < M ? ch_raw : M - 1;
   const long long r0 = chunk * (long long)chunk_rows;
   long long r1 = r0 + chunk_rows;
   if (r1 > nrows) r1 = nrows;
   const Thr t = thr[ch];
   const bool exact = t.ge == t.le;                        // threshold is itself a float: equality can occur
-  const unsigned long long chs = (unsigned long long)((ch + M / 2) % M);   // fftshift column (:60), even M
+  const unsigned long long chs = (unsigned long long)((ch + M / 2) % M);   // fftshift column (:60): k -> (k + floor(M/2)) mod M
   // state on entry = state after row r0-1 (0-based): mag > thr, except that exact equality toggles (:88,:94)
   bool active = false;
   if (live && r0 > 0) {
@@ -285,13 +288,13 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
   CHZ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)M * 2 * kBins * sizeof(uint32_t), st));
   lap("alloc");
   const uint32_t rank_lo = (uint32_t)((nrows - 1) / 2), rank_hi = (uint32_t)(nrows / 2);
-  long long ychunks = (h->sm_count * 4 + M / 4 - 1) / (M / 4);
+  long long ychunks = (h->sm_count * 4 + (M + 3) / 4 - 1) / ((M + 3) / 4);
   const long long max_chunks = (long long)((nrows + 255) / 256);
   if (ychunks > max_chunks) ychunks = max_chunks;
   if (ychunks < 1) ychunks = 1;
   if (ychunks > 65535) ychunks = 65535;
   for (int pass = 0; pass < 3; pass++) {
-    k_hist<<<dim3(M / 4, (unsigned)ychunks), 256, 0, st>>>(y, (long long)nrows, M, pass, d_sel, d_hist);
+    k_hist<<<dim3((M + 3) / 4, (unsigned)ychunks), 256, 0, st>>>(y, (long long)nrows, M, pass, d_sel, d_hist);
     k_select<<<M, 256, 0, st>>>(d_hist, d_sel, pass, rank_lo, rank_hi);
     h->launches += 2;
   }

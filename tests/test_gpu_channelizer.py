@@ -237,6 +237,26 @@ def test_edge_lengths_ragged_and_tiny(orc, M, P, os_, bw):
     ch.close()
 
 
+@pytest.mark.parametrize("M,P,os_,kind", [(56, 12, 1, "q11"), (56, 12, 2, "full"), (12, 8, 1, "i8"), (7, 5, 1, "full"),
+                                         (100, 16, 2, "full"), (560, 12, 1, "q11"), (4, 8, 1, "i8"), (2, 3, 2, "full")])
+def test_non_power_of_two_channel_counts(orc, M, P, os_, kind):
+    """The reference's own M is fs*1e-6 (56 for the b200mini at 56 MS/s, create_pdws_channelized.m:31);
+    such sizes run the functional any-M path.  Same tolerance, and streaming stays bit-identical."""
+    _torch()
+    n = M * 300 + 5
+    iq, bw = _gen(kind, n, M, seed=M)
+    taps = pkg.design_prototype(M, P)
+    ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=os_)
+    y = ch(iq, bw).copy()
+    ref = orc.channelize_raw(iq, bw, M, taps.astype(np.float64), os_)
+    assert y.shape == ref.shape == (n // (M // os_), M)
+    assert synth.rel_rms(y, ref) <= TOL
+    ch.reset()
+    parts = [ch(iq[a:b], bw).copy() for a, b in ((0, 3), (3, M * 7 + 1), (M * 7 + 1, M * 200), (M * 200, n))]
+    assert np.array_equal(np.concatenate(parts).view(np.float32), y.view(np.float32))
+    ch.close()
+
+
 def test_capacity_and_state_errors():
     torch = _torch()
     ch = pkg.Channelizer(64, NumTapsPerBand=16)

@@ -125,3 +125,26 @@ def test_end_to_end_pulsed_recording(orc, M, P, seed, tmp_path):
     assert len(pdw["toa"]) == len(orecs)
     assert np.allclose(pdw["toa"], [r.toa_s for r in orecs], atol=1.0 / (rec.fs / M) + 1e-9)
     assert np.array_equal(pdw["sat"], [bool(r.saturated) for r in orecs])
+
+
+def test_reference_script_defaults_m56(orc, tmp_path):
+    """create_pdws_channelized.m as written: M = fs*1e-6 = 56 bands at 56 MS/s, dsp.Channelizer(M) with the
+    toolbox defaults (12 taps per band, 80 dB), threshold 15 dB -- through the .iq reader and the script-level
+    entry point, against the oracle on the same bytes."""
+    _torch()
+    M, fs = 56, 56e6
+    n = M * 9000
+    iq, bw, _ = synth.pulsed_int16(n, M=M, seed=321, fs=fs)
+    path = str(tmp_path / "b200mini.iq")
+    pkg.write_iq(path, iq, fs=fs, fc=5.8e9, bitWidth=bw, sampleStartTime=1.7e9, fileFormat=3, boardName="b200mini")
+    pdw = pkg.create_pdws_channelized([path])                  # M and prototype from the file, like the script
+    rec = pkg.read_iq(path)
+    taps = orc.design_prototype(M, 12, 80.0)
+    oy = orc.channelize_raw(rec.iq, rec.bitWidth, M, taps)
+    orecs, _ = orc.pdws(oy, M, fc_hz=rec.fc, fs_sps=rec.fs, t0=rec.sampleStartTime)
+    assert len(orecs) >= 3 and len(pdw["toa"]) == len(orecs)
+    fs_dec = fs / M
+    assert np.allclose(pdw["toa"], [r.toa_s for r in orecs], atol=1.0 / fs_dec + 1e-9)
+    assert np.allclose(pdw["pw"], [r.pw_s for r in orecs], atol=1.0 / fs_dec + 1e-12)
+    assert np.array_equal(pdw["channel"], [r.channel for r in orecs])
+    assert np.allclose(pdw["freq"], [r.freq_hz for r in orecs], atol=1e-4 * fs_dec)
