@@ -92,7 +92,8 @@ int chz_design_prototype(uint32_t M, uint32_t taps_per_band, double stopband_att
 typedef struct chz chz_t;
 typedef struct chz_cf32 { float re, im; } chz_cf32;
 
-/* M: 2..4096.  Powers of two >= 8 run the tuned kernels; any other M (the reference's natural
+/* M: 1..4096.  M = 1 with the single tap 1.0 is the identity "channelizer" (unpack only), which
+ * makes chz_pdws the wideband extractor of matlab/create_pdws.m.  Powers of two >= 8 run the tuned kernels; any other M (the reference's natural
  * M = fs*1e-6 = 56, create_pdws_channelized.m:31) runs a functional direct-FIR + O(M^2) DFT path.
  * ntaps: positive multiple of M, ntaps/M <= 32; oversample 1 (D = M, critically sampled) or 2
  * (D = M/2, M even).  taps == NULL -> default prototype (12*M taps, 80 dB;
@@ -158,7 +159,8 @@ typedef struct chz_pdw_params {
   double fs_sps;               /* INPUT sample rate; the decimated rate fs/D is derived (:62)       */
   double t0;                   /* sampleStartTime (:98)                                             */
   uint32_t reproduce_phase_bug;/* 1: phase taken from shifted column 1 for every bin, as :114 does  */
-  uint32_t reserved;
+  uint32_t use_trailing_threshold; /* 1: hysteresis, trailing edge at trailing_snr_threshold_db         */
+  double trailing_snr_threshold_db;/* wideband script matlab/create_pdws.m:45-47: 18 dB up, 3 dB down   */
 } chz_pdw_params_t;
 
 typedef struct chz_pdw {

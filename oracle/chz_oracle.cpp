@@ -321,7 +321,8 @@ struct orc_pdw {
 };
 struct orc_pdw_params {
   double snr_threshold_db, sat_level, fc_hz, fs_sps, t0;
-  uint32_t reproduce_phase_bug, reserved;
+  uint32_t reproduce_phase_bug, use_trailing_threshold;
+  double trailing_snr_threshold_db;   // matlab/create_pdws.m:47 (wideband script: 3 dB)
 };
 
 static double median_of(std::vector<double>& v) {   // MATLAB median: mean of the middle two if even
@@ -352,6 +353,8 @@ uint64_t orc_pdws(const double* y, uint64_t nrows, uint32_t M, uint32_t D, const
     const double nf = median_of(tmp);                                     // :73
     if (noise_floor) noise_floor[k] = nf;
     const double thr = nf * thr_scale;                                    // :75
+    // wideband script (matlab/create_pdws.m:45-47,63): a separate, lower trailing-edge threshold
+    const double thr_trail = prm->use_trailing_threshold ? nf * std::pow(10.0, prm->trailing_snr_threshold_db / 10.0) : thr;
     const double fc_chan = prm->fc_hz + bin_freqs[bin];                   // :80
     bool active = false, saturated = false;                               // :82-83
     uint64_t toa = 0;
@@ -359,7 +362,7 @@ uint64_t orc_pdws(const double* y, uint64_t nrows, uint32_t M, uint32_t D, const
       const double mg = mag[jj - 1];
       if (!active) {                                                      // :87
         if (mg >= thr) { active = true; toa = jj; saturated = false; }    // :88-91
-      } else if (mg <= thr) {                                             // :94
+      } else if (mg <= thr_trail) {                                       // :94 (create_pdws.m:63)
         active = false;                                                   // :95
         orc_pdw r; memset(&r, 0, sizeof r);
         r.toa_s = ((double)toa / fs_dec) + prm->t0;                       // :98

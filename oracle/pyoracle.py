@@ -45,7 +45,7 @@ class Pdw(C.Structure):
 class PdwParams(C.Structure):
     _fields_ = [("snr_threshold_db", C.c_double), ("sat_level", C.c_double), ("fc_hz", C.c_double),
                 ("fs_sps", C.c_double), ("t0", C.c_double), ("reproduce_phase_bug", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("use_trailing_threshold", C.c_uint32), ("trailing_snr_threshold_db", C.c_double)]
 
 
 _lib = None
@@ -167,11 +167,12 @@ def center_frequencies(M, fs):
 
 
 def pdws(y, D, snr_threshold_db=15.0, sat_level=0.9999, fc_hz=0.0, fs_sps=1.0, t0=0.0,
-         reproduce_phase_bug=False):
+         reproduce_phase_bug=False, trailing_snr_threshold_db=None):
     """y complex128 [rows, M] natural order -> (list of Pdw, noise_floor[M] natural order)."""
     y = np.ascontiguousarray(y, dtype=np.complex128)
     rows, M = y.shape
-    prm = PdwParams(snr_threshold_db, sat_level, fc_hz, fs_sps, t0, int(reproduce_phase_bug), 0)
+    prm = PdwParams(snr_threshold_db, sat_level, fc_hz, fs_sps, t0, int(reproduce_phase_bug),
+                    0 if trailing_snr_threshold_db is None else 1, float(trailing_snr_threshold_db or 0.0))
     nf = np.empty(M, dtype=np.float64)
     n = lib().orc_pdws(_ptr(y), rows, M, D, C.byref(prm), None, 0, _ptr(nf))
     arr = (Pdw * max(n, 1))()

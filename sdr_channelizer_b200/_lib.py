@@ -40,7 +40,7 @@ class IqInfo(C.Structure):
 class PdwParams(C.Structure):
     _fields_ = [("snr_threshold_db", C.c_double), ("sat_level", C.c_double), ("fc_hz", C.c_double),
                 ("fs_sps", C.c_double), ("t0", C.c_double), ("reproduce_phase_bug", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("use_trailing_threshold", C.c_uint32), ("trailing_snr_threshold_db", C.c_double)]
 
 
 class Pdw(C.Structure):

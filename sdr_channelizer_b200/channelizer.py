@@ -227,17 +227,20 @@ class Channelizer:
         return [arr[i] for i in range(cnt)], nf
 
     def pdws(self, fs, fc=0.0, sampleStartTime=0.0, SNR_THRESHOLD=15.0, sat_level=0.9999,
-             reproduce_phase_bug=False):
+             reproduce_phase_bug=False, TRAILING_EDGE_THRESHOLD=None):
         """PDWs over everything processed since reset (create_pdws_channelized.m:60-136).
         -> (list of Pdw records in the reference's order, noise floor per natural channel)."""
-        prm = PdwParams(float(SNR_THRESHOLD), float(sat_level), float(fc), float(fs), float(sampleStartTime),
-                        int(bool(reproduce_phase_bug)), 0)
+        prm = self._params(fs, fc, sampleStartTime, SNR_THRESHOLD, sat_level, reproduce_phase_bug, TRAILING_EDGE_THRESHOLD)
         return self._pdw_call(lib().chz_pdws, prm)
 
+    @staticmethod
+    def _params(fs, fc, t0, snr, sat, bug, trailing):
+        return PdwParams(float(snr), float(sat), float(fc), float(fs), float(t0), int(bool(bug)),
+                         0 if trailing is None else 1, float(trailing or 0.0))
+
     def pdws_ptr(self, y_ptr, nrows, fs, fc=0.0, sampleStartTime=0.0, SNR_THRESHOLD=15.0, sat_level=0.9999,
-                 reproduce_phase_bug=False):
-        prm = PdwParams(float(SNR_THRESHOLD), float(sat_level), float(fc), float(fs), float(sampleStartTime),
-                        int(bool(reproduce_phase_bug)), 0)
+                 reproduce_phase_bug=False, TRAILING_EDGE_THRESHOLD=None):
+        prm = self._params(fs, fc, sampleStartTime, SNR_THRESHOLD, sat_level, reproduce_phase_bug, TRAILING_EDGE_THRESHOLD)
         return self._pdw_call(lib().chz_pdws_dev, prm, C.c_void_p(y_ptr), int(nrows))
 
 
@@ -279,5 +282,30 @@ def create_pdws_channelized(recordings, M=None, NumTapsPerBand=12, SNR_THRESHOLD
     return {k: np.asarray(v) for k, v in out.items()}
 
 
+def create_pdws(recordings, SNR_THRESHOLD=18.0, TRAILING_EDGE_THRESHOLD=3.0):
+    """matlab/create_pdws.m as a function: the wideband (un-channelized) extractor.  The raw stream is
+    normalised (:29-32) by a one-channel identity "channelizer" (K1 alone) and fed to the same PDW
+    kernels with hysteresis: leading edge at 18 dB over the median magnitude, trailing edge at 3 dB
+    (:44-47,58,63).  Returns dict(toa, freq, pw, mag, snr, sat) like the script's pdw struct (:86-91)."""
+    out = {k: [] for k in ("toa", "freq", "pw", "mag", "snr", "sat")}
+    for rec in recordings:
+        if not isinstance(rec, IqRecording):
+            rec = read_iq(rec)
+        ch = Channelizer(1, taps=np.ones(1, dtype=np.float32))
+        try:
+            n = C.c_uint64(0)
+            iq = np.ascontiguousarray(rec.iq)
+            check(lib().chz_process(ch.handle, iq.ctypes.data_as(C.c_void_p), iq.shape[0], rec.bitWidth,
+                                    None, 0, C.byref(n)), "chz_process")
+            recs, _ = ch.pdws(rec.fs, rec.fc, rec.sampleStartTime, SNR_THRESHOLD,
+                              TRAILING_EDGE_THRESHOLD=TRAILING_EDGE_THRESHOLD)
+        finally:
+            ch.close()
+        for r in recs:
+            out["toa"].append(r.toa_s); out["freq"].append(r.freq_hz); out["pw"].append(r.pw_s)
+            out["mag"].append(r.amp); out["snr"].append(r.snr_db); out["sat"].append(bool(r.saturated))
+    return {k: np.asarray(v) for k, v in out.items()}
+
+
 __all__ = ["IqRecording", "read_iq", "write_iq", "design_prototype", "Channelizer", "unpack_ptr",
-           "create_pdws_channelized", "ChannelizerError"]
+           "create_pdws_channelized", "create_pdws", "ChannelizerError"]

@@ -69,6 +69,7 @@ int main(int argc, char** argv) {
   prm.fc_hz = (double)info.fc_hz;
   prm.fs_sps = (double)info.fs_sps;
   prm.t0 = info.sample_start_time;
+  prm.use_trailing_threshold = 0;
   uint64_t npdw = 0;
   int status = chz_pdws(chan, &prm, nullptr, 0, &npdw);
   if (status != 0 && status != CHZ_ECAPACITY) CHECK(status);

@@ -458,7 +458,7 @@ int chz_abi_version(void) { return CHZ_ABI_VERSION; }
 int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversample, chz_t** out) {
   if (!out) return CHZ_EINVAL;
   *out = nullptr;
-  if (M < 2 || M > 4096) return CHZ_EINVAL;
+  if (M < 1 || M > 4096) return CHZ_EINVAL;
   if (oversample != 1 && oversample != 2) return CHZ_EINVAL;
   if (M % oversample != 0) return CHZ_EINVAL;
   if (taps && (ntaps == 0 || ntaps % M != 0 || ntaps / M > 32)) return CHZ_EINVAL;

@@ -107,7 +107,11 @@ __global__ void __launch_bounds__(256) k_select(uint32_t* __restrict__ hist, Sel
 }
 
 // ---- edge detection -----------------------------------------------------------------------------------
-struct Thr { float ge, le; };   // mag >= thr  <=>  mag >= ge ;  mag <= thr  <=>  mag <= le  (thr is a double)
+// Leading edge: mag >= T_lead <=> mag >= ge (ge = smallest float >= T_lead).  Trailing edge: mag <= T_trail <=>
+// mag <= le (le = largest float <= T_trail).  The channelized script uses one threshold for both
+// (create_pdws_channelized.m:88,94: T_trail == T_lead, ge/le bracket it); the wideband script uses
+// hysteresis (create_pdws.m:45-47,58,63: 18 dB up, 3 dB down => le < ge).
+struct Thr { float ge, le; };
 
 // Lanes walk channels (coalesced 8-byte loads of a row), all lanes advance row by row through the same
 // chunk, so a warp ballot per row tells whether any channel saw an edge; one atomic per warp reserves
@@ -135,20 +139,22 @@ __global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, lo
   long long r1 = r0 + chunk_rows;
   if (r1 > nrows) r1 = nrows;
   const Thr t = thr[ch];
-  const bool exact = t.ge == t.le;                        // threshold is itself a float: equality can occur
+  const bool exact = t.ge == t.le;                        // one threshold that is itself a float: equality can occur
   const unsigned long long chs = (unsigned long long)((ch + M / 2) % M);   // fftshift column (:60): k -> (k + floor(M/2)) mod M
-  // state on entry = state after row r0-1 (0-based): mag > thr, except that exact equality toggles (:88,:94)
+  // State on entry = state after row r0-1.  Walking back: a sample >= ge leaves the FSM active, one
+  // <= le leaves it inactive whatever came before; samples strictly between the two thresholds
+  // (hysteresis only) keep the earlier state; a sample exactly equal to a single representable threshold
+  // toggles it (:88 uses >=, :94 uses <= on the same value).
   bool active = false;
   if (live && r0 > 0) {
-    long long j = r0 - 1;
     bool flips = false;
-    float m = mag_of(y[j * M + ch]);
-    while (exact && m == t.ge) {
-      flips = !flips;
-      if (--j < 0) break;
-      m = mag_of(y[j * M + ch]);
+    for (long long j = r0 - 1; j >= 0; j--) {
+      const float m = mag_of(y[j * M + ch]);
+      if (exact && m == t.ge) { flips = !flips; continue; }
+      if (m >= t.ge) { active = true; break; }
+      if (m <= t.le) { active = false; break; }
     }
-    active = (j < 0 ? false : m > t.le) != flips;
+    active = active != flips;
   }
   for (int i = 0; i < chunk_rows; i++) {                  // lock-step over the chunk
     const long long r = r0 + i;
@@ -306,6 +312,11 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
   lap("median");
   // 2. thresholds (:74-75), double on the host, bracketed by floats for the fp32 comparisons
   const double scale = std::pow(10.0, prm->snr_threshold_db / 10.0);
+  // create_pdws.m:47: TRAILING_EDGE_THRESHOLD = NOISE_FLOOR*10^(3/10); never above the leading threshold
+  const bool hyst = prm->use_trailing_threshold != 0 && prm->trailing_snr_threshold_db < prm->snr_threshold_db;
+  const double scale_lo = hyst ? std::pow(10.0, prm->trailing_snr_threshold_db / 10.0) : scale;
+  auto float_ge = [](double t) { float f = (float)t; return (double)f < t ? std::nextafterf(f, INFINITY) : f; };
+  auto float_le = [](double t) { float f = (float)t; return (double)f > t ? std::nextafterf(f, -INFINITY) : f; };
   std::vector<Thr> thr(M);
   for (int k = 0; k < M; k++) {
     float lo, hi;
@@ -313,12 +324,8 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
     memcpy(&hi, &sel[k].prefix[1], 4);
     const double nf = 0.5 * ((double)lo + (double)hi);     // MATLAB median: mean of the two middle values
     h->noise_floor[k] = nf;
-    const double t = nf * scale;
-    float f = (float)t;                                    // round to nearest
-    float ge = f, le = f;
-    if ((double)f < t) ge = std::nextafterf(f, INFINITY);
-    else if ((double)f > t) le = std::nextafterf(f, -INFINITY);
-    thr[k].ge = ge; thr[k].le = le;
+    thr[k].ge = float_ge(nf * scale);
+    thr[k].le = float_le(nf * scale_lo);
   }
   CHZ_CUDA(cudaMemcpyAsync(d_thr, thr.data(), sizeof(Thr) * M, cudaMemcpyHostToDevice, st));
 

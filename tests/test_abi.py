@@ -111,7 +111,7 @@ def test_prototype_matches_oracle(orc, M, P):
 def test_create_argument_checks_and_no_cpu_fallback():
     L = pkg.lib()
     h = C.c_void_p()
-    for M in (0, 1, 4097, 8192):
+    for M in (0, 4097, 8192):
         assert L.chz_create(M, None, 0, 1, C.byref(h)) == _lib.CHZ_EINVAL
     assert L.chz_create(7, None, 0, 2, C.byref(h)) == _lib.CHZ_EINVAL      # 2x oversampling needs an even M
     assert L.chz_create(64, None, 0, 3, C.byref(h)) == _lib.CHZ_EINVAL

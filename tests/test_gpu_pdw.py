@@ -21,7 +21,7 @@ def _pdws_on_matrix(y, fs, **kw):
     torch = _torch()
     M = y.shape[1]
     d = torch.from_numpy(np.ascontiguousarray(y.astype(np.complex64))).cuda()
-    ch = pkg.Channelizer(M, NumTapsPerBand=8)
+    ch = pkg.Channelizer(M, NumTapsPerBand=8) if M > 1 else pkg.Channelizer(1, taps=np.ones(1, np.float32))
     ch.set_stream(torch.cuda.current_stream().cuda_stream)
     recs, nf = ch.pdws_ptr(d.data_ptr(), y.shape[0], fs, **kw)
     ch.close()
@@ -148,3 +148,29 @@ def test_reference_script_defaults_m56(orc, tmp_path):
     assert np.allclose(pdw["pw"], [r.pw_s for r in orecs], atol=1.0 / fs_dec + 1e-12)
     assert np.array_equal(pdw["channel"], [r.channel for r in orecs])
     assert np.allclose(pdw["freq"], [r.freq_hz for r in orecs], atol=1e-4 * fs_dec)
+
+
+def test_wideband_create_pdws_script(orc, tmp_path):
+    """matlab/create_pdws.m end to end: raw stream -> normalise (K1 via the one-channel identity
+    channelizer) -> hysteresis detector (18 dB / 3 dB) -> per-pulse medians, against the oracle."""
+    _torch()
+    fs, n = 10e6, 400_000
+    x, meta = synth.pulsed_complex(n, fs, seed=77, sigma=0.004, amp=0.6)
+    iq = np.stack([np.clip(np.rint(x.real * 32768), -32768, 32767), np.clip(np.rint(x.imag * 32768), -32768, 32767)],
+                  axis=1).astype(np.int16)
+    path = str(tmp_path / "wide.iq")
+    pkg.write_iq(path, iq, fs=fs, fc=915e6, bitWidth=16, sampleStartTime=100.0)
+    pdw = pkg.create_pdws([path])
+    y = orc.unpack(iq, 16).reshape(-1, 1)
+    orecs, onf = orc.pdws(y, 1, snr_threshold_db=18.0, fc_hz=915e6, fs_sps=fs, t0=100.0, trailing_snr_threshold_db=3.0)
+    assert len(orecs) >= 3 and len(pdw["toa"]) == len(orecs)
+    assert np.allclose(pdw["toa"], [r.toa_s for r in orecs], atol=1.0 / fs + 1e-9)
+    assert np.allclose(pdw["pw"], [r.pw_s for r in orecs], atol=1.0 / fs + 1e-12)
+    assert np.allclose(pdw["mag"], [r.amp for r in orecs], rtol=1e-5)
+    assert np.allclose(pdw["freq"], [r.freq_hz for r in orecs], atol=1e-4 * fs)
+    assert np.array_equal(pdw["sat"], [bool(r.saturated) for r in orecs])
+    # hysteresis known answer on the device matrix path
+    t = np.full(2000, 0.01 + 0j, dtype=np.complex64)
+    t[500:600] = 0.9; t[600:650] = 0.05; t[650] = 0.0101; t[900:905] = 0.8
+    recs, _ = _pdws_on_matrix(t.reshape(-1, 1), 1e6, SNR_THRESHOLD=18.0, TRAILING_EDGE_THRESHOLD=3.0)
+    assert [(r.toa_row, r.end_row) for r in recs] == [(501, 651), (901, 906)]

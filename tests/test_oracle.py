@@ -234,3 +234,20 @@ def test_pdws_phase_bug_flag(orc):
     for r in bug:
         assert abs((r.freq_hz - cf[r.channel]) - fs_dec * np.degrees(0.5) / 360.0) < 1.0
     assert abs((good[1].freq_hz - cf[good[1].channel]) - fs_dec * np.degrees(0.3) / 360.0) < 0.02 * fs_dec
+
+
+def test_wideband_hysteresis_thresholds(orc):
+    """matlab/create_pdws.m:45-47,58,63: leading edge at 18 dB over the median, trailing edge at 3 dB.
+    One column (the un-channelized stream), D = 1."""
+    n = 2000
+    x = np.full(n, 0.01 + 0j)
+    x[500:600] = 0.9                      # strong pulse
+    x[600:650] = 0.05                     # sags below the leading but above the 3 dB trailing threshold: still active
+    x[650] = 0.0101                       # <= trailing threshold (0.01 * 10^0.3 = 0.01995) -> trailing edge
+    x[900:905] = 0.8
+    recs, nf = orc.pdws(x.reshape(-1, 1), 1, snr_threshold_db=18.0, fs_sps=1e6, trailing_snr_threshold_db=3.0)
+    assert nf[0] == 0.01
+    assert [(r.toa_row, r.end_row) for r in recs] == [(501, 651), (901, 906)]
+    # with the single 18 dB threshold the first pulse ends as soon as it sags
+    recs1, _ = orc.pdws(x.reshape(-1, 1), 1, snr_threshold_db=18.0, fs_sps=1e6)
+    assert [(r.toa_row, r.end_row) for r in recs1] == [(501, 601), (901, 906)]
