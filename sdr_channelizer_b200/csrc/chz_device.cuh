@@ -2,6 +2,9 @@
 //   K1  raw int8/int16 I/Q -> fp32 (exact; matlab/create_pdws_channelized.m:35-38)
 //   K3  in-register DFT-2/4/8/16 and the shared-memory Stockham FFT over polyphase branches
 #pragma once
+#ifndef CHZ_TWREG
+#define CHZ_TWREG 1
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -170,7 +173,7 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, fl
 template <int M, int NT> struct TwReg {
   typedef Plan<M> PL;
   static constexpr int RL = PL::np == 2 ? PL::r1 : 1;                 // radix of the last pass
-  static constexpr bool value = PL::np == 2 && RL <= 8 && (NT % (M / RL) == 0);
+  static constexpr bool value = CHZ_TWREG && PL::np == 2 && RL <= 8 && (NT % (M / RL) == 0);
   static constexpr int count = value ? RL - 1 : 1;
 };
 // Per-thread twiddles of the last pass of a two-pass plan: W_{r0 r1}^{q (j mod r0)}, q = 1..r1-1
