@@ -209,6 +209,36 @@ static int launch_fused_dispatch(::chz* h, const ChanParams& prm, cudaStream_t s
   }
 }
 
+// M = 1024 on CTA pairs (decimation-in-time split over DSMEM).
+template <int P, bool IN16>
+static int launch_dit2(::chz* h, ChanParams prm, cudaStream_t st) {
+  typedef Dit2Cfg<P> DC;
+  auto kern = k_chan_dit2<P, IN16>;
+  static thread_local bool attr = false;
+  if (!attr) {
+    CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DC::SMEM));
+    attr = true;
+  }
+  const int nclusters = h->sm_count / 2;                       // one 512-thread CTA per SM
+  const LaunchPlan lp = plan_spans(h, prm.nrows, P, 1, 1, nclusters);
+  prm.span_rows = lp.span_rows;
+  prm.spans_per_phase = lp.spans_per_phase;
+  kern<<<lp.grid.x * 2, 512, DC::SMEM, st>>>(prm);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  return CHZ_OK;
+}
+template <bool IN16>
+static int launch_dit2_dispatch(::chz* h, const ChanParams& prm, cudaStream_t st) {
+  switch (h->P) {
+    case 8: return launch_dit2<8, IN16>(h, prm, st);
+    case 12: return launch_dit2<12, IN16>(h, prm, st);
+    case 16: return launch_dit2<16, IN16>(h, prm, st);
+    default: return 1;
+  }
+}
+static bool dit2_available(const ::chz* h) { return h->M == 1024 && (h->P == 8 || h->P == 12 || h->P == 16); }
+
 // Warp-specialised fused kernel (M = 64).
 template <int P, bool IN16>
 static int launch_ws(::chz* h, ChanParams prm, cudaStream_t st) {
@@ -337,7 +367,12 @@ static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, 
     const bool ws = ws_available(h) && h->force_path == 4;
     if (h->force_path == 4 && !ws) return CHZ_EINVAL;
     if (h->force_path == 1 && !fused) return CHZ_EINVAL;
-    if (ws) {
+    const bool dit2 = dit2_available(h) && h->force_path == 5;
+    if (h->force_path == 5 && !dit2) return CHZ_EINVAL;
+    if (dit2) {
+      rc = in16 ? launch_dit2_dispatch<true>(h, prm, st) : launch_dit2_dispatch<false>(h, prm, st);
+      if (rc) return rc == 1 ? CHZ_EINVAL : rc;
+    } else if (ws) {
       rc = in16 ? launch_ws_dispatch<true>(h, prm, st) : launch_ws_dispatch<false>(h, prm, st);
       if (rc) return rc == 1 ? CHZ_EINVAL : rc;
     } else     if (cluster) {
@@ -586,7 +621,7 @@ int chz_set_option(chz_t* h, int opt, int64_t value) {
   switch (opt) {
     case CHZ_OPT_RETAIN: h->retain = value != 0; return CHZ_OK;
     case CHZ_OPT_CHUNK_ROWS: if (value < 0) return CHZ_EINVAL; h->chunk_rows = value; return CHZ_OK;
-    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 4) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
+    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 5) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
     default: return CHZ_EINVAL;
   }
 }

@@ -556,4 +556,108 @@ __global__ void __launch_bounds__(512, 1) k_chan_cluster(ChanParams prm, float2*
   }
 }
 
+// ---- M = 1024 fused on CTA pairs: decimation-in-time split over distributed shared memory ----------
+// 1024 branch windows do not fit one SM's registers, 512 do.  A cluster of two CTAs splits the branches
+// by parity: CTA c filters branches p = 2t + c (t = thread) with the usual register windows, runs a
+// 512-point FFT of its half in shared memory and leaves E = FFT512(even part) or O = FFT512(odd part)
+// in a result buffer.  After ONE cluster barrier per tile the last radix-2 stage
+//     Y[k] = E[k] + W_1024^k O[k],   Y[k + 512] = E[k] - W_1024^k O[k]
+// is computed by both CTAs, each for 256 values of k, reading the partner's half through DSMEM
+// (ld.shared::cluster) and storing two contiguous 2 KB runs per row.  Only half of the FFT output
+// crosses the SM-to-SM network (4 B per output sample); DRAM traffic is the algorithmic minimum.
+// The price: each CTA touches every input sector but uses half of it (8 instead of 4 B per sample
+// from L2).  Result buffers are double buffered, so one barrier per tile suffices.
+template <int P> struct Dit2Cfg {
+  static constexpr int MS = 512;                                   // sub-FFT size
+  static constexpr int RT = (P % 8 == 0) ? 8 : 4;                  // rows per FFT tile (divides P, even)
+  static constexpr int S = RowStride<MS>::value;
+  static constexpr size_t SMEM = ((size_t)2 * RT * S + 2 * RT * MS + MS) * sizeof(float2);
+};
+
+__device__ __forceinline__ float2 ld_dsmem(const float2* local, unsigned peer) {
+  unsigned la = (unsigned)__cvta_generic_to_shared(local), ra;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(peer));
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra));
+  return v;
+}
+
+template <int P, bool IN16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) k_chan_dit2(ChanParams prm) {
+  constexpr int M = 1024, MS = Dit2Cfg<P>::MS, RT = Dit2Cfg<P>::RT, S = Dit2Cfg<P>::S;
+  typedef Plan<MS> PL;                                             // 512 = 16 * 8 * 4
+  extern __shared__ float2 smem[];
+  float2* buf0 = smem;                                             // [RT][S]
+  float2* buf1 = buf0 + RT * S;
+  float2* res = buf1 + RT * S;                                     // [2][RT][MS]  E or O, natural order
+  float2* tw = res + 2 * RT * MS;                                  // twiddles of the 512-point plan
+  const int t = threadIdx.x;
+  const unsigned rank = cluster_ctarank();
+  {  // inter-pass twiddles, layout (q-1)*NS + k (see stockham_pass): pass 2 (NS=16, R=8), pass 3 (NS=128, R=4)
+    constexpr int N2 = (PL::r1 - 1) * PL::r0, N3 = (PL::r2 - 1) * PL::r0 * PL::r1;
+    for (int i = t; i < N2 + N3; i += 512) {
+      int q, k, n;
+      if (i < N2) { q = i / PL::r0 + 1; k = i % PL::r0; n = PL::r0 * PL::r1; }
+      else { const int e = i - N2; q = e / (PL::r0 * PL::r1) + 1; k = e % (PL::r0 * PL::r1); n = PL::r0 * PL::r1 * PL::r2; }
+      float sn, cs;
+      sincospif(2.0f * (float)(q * k) / (float)n, &sn, &cs);
+      tw[i] = make_float2(cs, sn);
+    }
+  }
+  // last (radix-2) stage: this thread owns k = 256 rank + kl for the rows of its parity
+  const int kl = t & 255, rpar = t >> 8;
+  const int kk = 256 * (int)rank + kl;
+  float2 wk;
+  sincospif((float)kk / 512.0f, &wk.y, &wk.x);                     // W_1024^k = e^{+j 2 pi k / 1024}
+  __syncthreads();
+  const int p = 2 * t + (int)rank;
+  const long long cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const long long nspans = prm.spans_per_phase * prm.os;
+  const long long rstride = (long long)prm.os * M;
+  unsigned tile = 0;
+  for (long long s = cid; s < nspans; s += ncl) {                  // cluster-uniform
+    const Span sp = make_span(prm, s);
+    if (sp.count <= 0) continue;
+    const int rs = padi<MS>(((p - sp.shift + M) % M) >> 1);        // position in this CTA's half-sequence
+    float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
+    fir_span<P, IN16, M, 0>(prm, sp, p, [&](int ii, long long i, float2 v) {
+      buf0[(ii % RT) * S + rs] = v;
+      if (ii % RT == RT - 1) {
+        float2* rb = res + (size_t)(tile & 1) * RT * MS;
+        __syncthreads();
+        stockham_pass<MS, PL::r0, 1, RT, 512, false, false>(buf0, buf1, tw, nullptr, t, nullptr, 0, 0, 0);
+        __syncthreads();
+        stockham_pass<MS, PL::r1, PL::r0, RT, 512, false, false>(buf1, buf0, tw, nullptr, t, nullptr, 0, 0, 0);
+        __syncthreads();
+        stockham_pass<MS, PL::r2, PL::r0 * PL::r1, RT, 512, true, false>(buf0, buf1, tw, nullptr, t, rb, (long long)MS, 0, RT);
+        cluster_barrier();                                         // both halves' results are in place
+        const long long i0 = i - (RT - 1);
+        const long long left = sp.count - i0;
+        const int vhi = (int)(left < RT ? (left < 0 ? 0 : left) : RT);
+        const int vlo = i0 < sp.skip ? (int)(sp.skip - i0) : 0;
+        // all DSMEM loads of this thread's rows are issued before any is used (each costs ~200+ cycles)
+        float2 ea[RT / 2], ob[RT / 2];
+        #pragma unroll
+        for (int u = 0; u < RT / 2; u++) {
+          const float2* mine = rb + (rpar + 2 * u) * MS + kk;
+          ea[u] = rank == 0 ? *mine : ld_dsmem(mine, 0);           // E[k]
+          ob[u] = rank == 1 ? *mine : ld_dsmem(mine, 1);           // O[k]
+        }
+        #pragma unroll
+        for (int u = 0; u < RT / 2; u++) {
+          const int r = rpar + 2 * u;
+          const float2 o = cmul(ob[u], wk);
+          if (r >= vlo && r < vhi) {
+            float2* g = gout + (i0 + r) * rstride + kk;
+            g[0] = cadd(ea[u], o);
+            g[MS] = csub(ea[u], o);
+          }
+        }
+        tile++;
+      }
+    });
+  }
+  cluster_barrier();   // do not exit while the partner may still read this CTA's shared memory
+}
+
 }  // namespace chzi

@@ -105,7 +105,8 @@ def test_channelizer_matches_oracle(orc, M, P, os_, kind, n):
 @pytest.mark.parametrize("M,P,os_,path", [(64, 16, 1, 1), (64, 16, 2, 1), (64, 12, 1, 1), (8, 8, 1, 1), (256, 16, 1, 1),
                                           (512, 8, 2, 1), (32, 12, 2, 1), (128, 16, 1, 1), (16, 16, 1, 1),
                                           (64, 16, 1, 2), (1024, 16, 2, 0), (4096, 8, 1, 0), (64, 24, 1, 0), (64, 32, 2, 0),
-                                          (4096, 16, 1, 3), (2048, 16, 2, 3), (1024, 8, 1, 3), (64, 16, 1, 4), (64, 16, 2, 4), (64, 12, 1, 4), (64, 8, 2, 4)])
+                                          (4096, 16, 1, 3), (2048, 16, 2, 3), (1024, 8, 1, 3), (64, 16, 1, 4), (64, 16, 2, 4), (64, 12, 1, 4), (64, 8, 2, 4),
+                                          (1024, 16, 1, 5), (1024, 16, 2, 5), (1024, 12, 2, 5), (1024, 8, 1, 5)])
 def test_random_taps_every_tap_index_matters(orc, M, P, os_, path):
     """A designed prototype has tiny end taps, which would hide a mis-indexed tap or window slot
     below the 1e-5 tolerance; with random taps of equal weight any such slip is an O(1/P) error."""

@@ -48,6 +48,8 @@ def run_chan(name, scale, steps):
     rows = n // (M // os_)
     y = torch.empty((rows, M), dtype=torch.complex64, device=dev)
     ch = pkg.Channelizer(M, taps=pkg.design_prototype(M, P), OversamplingRatio=os_)
+    if os.environ.get("CHZ_BENCH_PATH"):          # kernel A/B experiments
+        ch.set_option(pkg.CHZ_OPT_FORCE_PATH, int(os.environ["CHZ_BENCH_PATH"]))
     st = torch.cuda.Stream()
     torch.cuda.synchronize()
     with torch.cuda.stream(st):
