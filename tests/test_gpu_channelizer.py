@@ -278,20 +278,25 @@ def test_capacity_and_state_errors():
 
 
 # ---- size-independent properties at (near) BASELINE size ------------------------------------------------
-def test_large_run_spot_rows_and_linearity(orc):
-    """configs[1] geometry on ~0.6 s of 61.44 MS/s (37.7 M samples, device resident): random rows are
-    checked against the oracle evaluated on just the samples those rows touch, and the transform is
-    linear: chan(a) + chan(b) == chan(a + b) when a + b does not clip."""
+@pytest.mark.parametrize("M,P,os_,bw,nframes", [(64, 16, 1, 12, 589_000),      # configs[1] geometry, 37.7 M samples
+                                               (4096, 16, 1, 12, 22_000),     # configs[3] geometry, 90.1 M samples
+                                               (1024, 16, 2, 16, 40_000),     # configs[2] geometry, 41.0 M samples
+                                               (256, 16, 1, 16, 175_000)])    # configs[4] geometry, 44.8 M samples
+def test_large_run_spot_rows_and_linearity(orc, M, P, os_, bw, nframes):
+    """BASELINE geometries at sizes the oracle cannot run whole: random rows are checked against the
+    oracle evaluated on just the samples those rows touch, and the transform is linear:
+    chan(a) + chan(b) == chan(a + b) when a + b does not clip."""
     torch = _torch()
-    M, P, bw = 64, 16, 12
-    n = 64 * 589_000
+    n = M * nframes
+    D, L = M // os_, M * P
+    lim = 2 ** (bw - 1) // 2 - 1
     g = torch.Generator(device="cuda").manual_seed(5)
-    a = torch.randint(-900, 900, (n, 2), dtype=torch.int16, device="cuda", generator=g)
-    b = torch.randint(-900, 900, (n, 2), dtype=torch.int16, device="cuda", generator=g)
+    a = torch.randint(-lim, lim, (n, 2), dtype=torch.int16, device="cuda", generator=g)
+    b = torch.randint(-lim, lim, (n, 2), dtype=torch.int16, device="cuda", generator=g)
     taps = pkg.design_prototype(M, P)
-    ch = pkg.Channelizer(M, taps=taps)
+    ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=os_)
     ch.set_stream(torch.cuda.current_stream().cuda_stream)
-    rows = n // M
+    rows = n // D
     outs = []
     for src in (a, b, a + b):
         ch.reset()
@@ -302,14 +307,15 @@ def test_large_run_spot_rows_and_linearity(orc):
     lin = (torch.linalg.norm(outs[0] + outs[1] - outs[2]) / torch.linalg.norm(outs[2])).item()
     assert lin < 1e-6, lin
     rng = np.random.default_rng(0)
-    L = M * P
-    for m in [0, 1, P - 1, rows - 1] + [int(v) for v in rng.integers(P, rows, 24)]:
-        lo = max(0, m * M - (L - 1))
-        seg = a[lo:m * M + 1].cpu().numpy()                                   # x[mM-L+1 .. mM], clipped at 0
+    for m in [0, 1, 2, os_ * P - 1, rows - 2, rows - 1] + [int(v) for v in rng.integers(P, rows, 18)]:
+        lo = max(0, m * D - (L - 1))
+        seg = a[lo:m * D + 1].cpu().numpy()                                   # x[mD-L+1 .. mD], clipped at 0
         seg_full = np.concatenate([np.zeros((L - len(seg), 2), np.int16), seg])
-        # window with x[mM] at index L = P*M: its row P is row m of the full run
-        win = np.concatenate([np.zeros((1, 2), np.int16), seg_full, np.zeros((M - 1, 2), np.int16)])
-        ref = orc.channelize_raw(win, bw, M, taps.astype(np.float64))[P]
+        # window in which x[mD] sits at index idx = L + (mD mod M): same frame and rotation phase as in
+        # the full run, complete FIR history before it; its row idx/D is row m of the full run
+        idx = L + (m * D) % M
+        win = np.concatenate([np.zeros((idx - (L - 1), 2), np.int16), seg_full, np.zeros((D - 1, 2), np.int16)])
+        ref = orc.channelize_raw(win, bw, M, taps.astype(np.float64), os_)[idx // D]
         got = outs[0][m].cpu().numpy()
         assert synth.rel_rms(got, ref) <= TOL, m
     ch.close()
