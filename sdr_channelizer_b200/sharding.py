@@ -59,3 +59,32 @@ def stitch_rows(parts):
     """Concatenate per-shard row blocks (already trimmed of their discard rows) in rank order."""
     import numpy as np
     return np.concatenate(list(parts), axis=0) if parts else None
+
+
+def gather_rows_to_rank(y_local, rows_per_rank, dst=0, group=None):
+    """Multi-GPU PDW stage, simplest exact form: the PDW threshold is the per-channel
+    median of |y| over the WHOLE recording (create_pdws_channelized.m:73), so the time shards' channel
+    matrices are collected on one GPU over NCCL/NVLink (gather in time order) and chz_pdws_dev runs there
+    on the stitched matrix.  y_local: torch complex64 [rows, M] on this rank's GPU; rows_per_rank: list
+    of every rank's row count.  Returns the stitched [sum(rows), M] tensor on `dst`, None elsewhere.
+    (A distributed median by histogram all-reduce would avoid moving y; not built yet.)"""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    M = y_local.shape[1]
+    if rank == dst:
+        out = torch.empty((sum(rows_per_rank), M), dtype=y_local.dtype, device=y_local.device)
+        parts, pos = [], 0
+        for r in rows_per_rank:
+            parts.append(out[pos:pos + r]); pos += r
+    else:
+        out, parts = None, None
+    # rows differ by at most one between ranks: exchange as float32 views with point-to-point copies in rank order
+    if rank == dst:
+        parts[dst].copy_(y_local)
+        reqs = [dist.irecv(torch.view_as_real(parts[r]), src=r, group=group) for r in range(world) if r != dst]
+        for q in reqs:
+            q.wait()
+    else:
+        dist.send(torch.view_as_real(y_local.contiguous()), dst=dst, group=group)
+    return out

@@ -70,3 +70,31 @@ def test_two_rank_gloo_sharded_equals_unsharded(tmp_path, orc, M, P, os_):
     whole = orc.channelize_raw(iq, bw, M, orc.design_prototype(M, P), os_)
     got = np.load(out_path)
     assert got.shape == whole.shape and np.array_equal(got, whole)
+
+
+def _gather_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sdr_channelizer_b200.sharding import gather_rows_to_rank
+    rows = [5, 4, 4][:world]
+    g = torch.Generator().manual_seed(rank)
+    y = torch.complex(torch.randn(rows[rank], 8, generator=g), torch.randn(rows[rank], 8, generator=g))
+    full = gather_rows_to_rank(y, rows, dst=0)
+    if rank == 0:
+        torch.save(full, out_path)
+    else:
+        assert full is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_rows_in_time_order_gloo(tmp_path):
+    """The PDW stage's one exchange: shard row blocks collected on rank 0 in rank (= time) order."""
+    out_path = str(tmp_path / "full.pt")
+    mp.spawn(_gather_worker, args=(3, _free_port(), out_path), nprocs=3, join=True)
+    full = torch.load(out_path)
+    expect = []
+    for r, n in enumerate([5, 4, 4]):
+        g = torch.Generator().manual_seed(r)
+        expect.append(torch.complex(torch.randn(n, 8, generator=g), torch.randn(n, 8, generator=g)))
+    assert torch.equal(full, torch.cat(expect))
