@@ -392,17 +392,39 @@ static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, 
       long long chunk_rows = (long long)(h->split_chunk_bytes / ((uint64_t)h->M * sizeof(float2)));
       chunk_rows &= ~1LL;                       // even: row pairs stay aligned to global parity
       if (chunk_rows < 2) chunk_rows = 2;
-      for (long long r0 = 0; r0 < (long long)rows_new; r0 += chunk_rows) {
+      const long long nchunks = ((long long)rows_new + chunk_rows - 1) / chunk_rows;
+      const bool overlap = nchunks > 2 && h->split_overlap;
+      if (overlap && !h->ev_fir[0]) {
+        for (int i = 0; i < 4; i++) {
+          CHZ_CUDA(cudaEventCreateWithFlags(&h->ev_fir[i], cudaEventDisableTiming));
+          CHZ_CUDA(cudaEventCreateWithFlags(&h->ev_fft[i], cudaEventDisableTiming));
+        }
+      }
+      // overlap mode: FIR(i+1) on the main stream runs concurrently with FFT(i) on a side stream, at most two
+      // chunks ahead, so the two small kernels fill each other's launch gaps and tails
+      cudaStream_t sb = overlap ? h->s_h2d : st;
+      long long ci = 0;
+      for (long long r0 = 0; r0 < (long long)rows_new; r0 += chunk_rows, ci++) {
         const long long nr = std::min<long long>(chunk_rows, (long long)rows_new - r0);
         ChanParams cp = prm;
         cp.row_base = prm.row_base + r0;
         cp.nrows = nr;
         float2* dst = out_dev + r0 * (long long)h->M;
         cp.out = dst;
+        if (overlap && ci >= 2) CHZ_CUDA(cudaStreamWaitEvent(st, h->ev_fft[(ci - 2) & 3], 0));
         rc = in16 ? launch_fir_dispatch<true>(h, cp, dst, st) : launch_fir_dispatch<false>(h, cp, dst, st);
         if (rc) return rc;
-        rc = launch_fft_rows(h, dst, dst, nr, st);
+        if (overlap) {
+          CHZ_CUDA(cudaEventRecord(h->ev_fir[ci & 3], st));
+          CHZ_CUDA(cudaStreamWaitEvent(sb, h->ev_fir[ci & 3], 0));
+        }
+        rc = launch_fft_rows(h, dst, dst, nr, sb);
         if (rc) return rc;
+        if (overlap) CHZ_CUDA(cudaEventRecord(h->ev_fft[ci & 3], sb));
+      }
+      if (overlap) {   // the main stream continues only after the last FFTs
+        CHZ_CUDA(cudaStreamWaitEvent(st, h->ev_fft[(ci - 1) & 3], 0));
+        if (ci >= 2) CHZ_CUDA(cudaStreamWaitEvent(st, h->ev_fft[(ci - 2) & 3], 0));
       }
     }
   }
@@ -561,6 +583,7 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
   }
   CHZ_TRY(cudaMalloc(&h->d_tw, sizeof(float2) * M));
   CHZ_TRY(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+  if (const char* e = std::getenv("CHZ_SPLIT_OVERLAP")) h->split_overlap = std::atoi(e) != 0;   // tuning aid
   if (const char* e = std::getenv("CHZ_SPLIT_CHUNK_MB")) {   // tuning aid
     const long v = std::atol(e);
     if (v > 0) h->split_chunk_bytes = (uint64_t)v << 20;
@@ -592,6 +615,7 @@ void chz_destroy(chz_t* h) {
   if (h->d_store) cudaFree(h->d_store);
   if (h->d_u) cudaFree(h->d_u);
   h->cluster_ring.release();
+  for (int i = 0; i < 4; i++) { if (h->ev_fir[i]) cudaEventDestroy(h->ev_fir[i]); if (h->ev_fft[i]) cudaEventDestroy(h->ev_fft[i]); }
   for (chzi::Scratch* sc : {&h->pdw_hist, &h->pdw_sel, &h->pdw_thr, &h->pdw_cnt, &h->pdw_ev, &h->pdw_pin, &h->pdw_pout}) sc->release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);

@@ -80,6 +80,8 @@ struct chz {
   int64_t chunk_rows = 0;
 
   int force_path = 0;
+  bool split_overlap = false;                 // split path: run FFT(i) on a side stream under FIR(i+1)
+  cudaEvent_t ev_fir[4] = {nullptr, nullptr, nullptr, nullptr}, ev_fft[4] = {nullptr, nullptr, nullptr, nullptr};
   uint64_t split_chunk_bytes = 1ull << 40;    // split path: FIR output bytes per launch pair (CHZ_SPLIT_CHUNK_MB)
   uint64_t launches = 0;
 
