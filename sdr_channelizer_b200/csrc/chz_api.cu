@@ -24,6 +24,7 @@ void set_cuda_error(cudaError_t e, const char* what, const char* file, int line)
 // launch tables
 // ------------------------------------------------------------------------------------------------
 struct LaunchPlan { dim3 grid; int span_rows; long long spans_per_phase; };
+constexpr int kMaxDev = 64;   // function attributes (dynamic smem size) and occupancy are per device
 
 static LaunchPlan plan_spans(const ::chz* h, long long nrows, int P, int groups_per_block, int blocks_per_sm,
                              int max_blocks_override = 0) {
@@ -50,7 +51,8 @@ template <int M, int P, bool IN16>
 static int launch_fused(::chz* h, ChanParams prm, cudaStream_t st) {
   typedef FusedCfg<M, P> CF;
   auto kern = k_chan_fused<M, P, IN16>;
-  static thread_local int blocks_per_sm = 0;
+  static thread_local int blocks_per_sm_dev[kMaxDev] = {0};   // launch geometry is cached per device
+  int& blocks_per_sm = blocks_per_sm_dev[h->device % kMaxDev];
   if (!blocks_per_sm) {
     CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
     int nb = 0;
@@ -96,7 +98,8 @@ template <int M, int ROWS, int NT>
 static int launch_fft_rows_t(::chz* h, const float2* u, float2* y, long long nrows, cudaStream_t st) {
   auto kern = k_fft_rows<M, ROWS, NT>;
   const size_t smem = (size_t)(2 * ROWS * RowStride<M>::value + M) * sizeof(float2);
-  static thread_local int blocks_per_sm = 0;
+  static thread_local int blocks_per_sm_dev[kMaxDev] = {0};   // launch geometry is cached per device
+  int& blocks_per_sm = blocks_per_sm_dev[h->device % kMaxDev];
   if (!blocks_per_sm) {
     CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
@@ -117,7 +120,8 @@ template <int M, int ROWS>
 static int launch_fft_rows_big(::chz* h, const float2* u, float2* y, long long nrows, cudaStream_t st) {
   auto kern = k_fft_rows_big<M, ROWS>;
   const size_t smem = (size_t)(2 * ROWS * RowStride<M>::value) * sizeof(float2);
-  static thread_local int blocks_per_sm = 0;
+  static thread_local int blocks_per_sm_dev[kMaxDev] = {0};   // launch geometry is cached per device
+  int& blocks_per_sm = blocks_per_sm_dev[h->device % kMaxDev];
   if (!blocks_per_sm) {
     CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
@@ -138,7 +142,8 @@ static int launch_fft_rows(::chz* h, const float2* u, float2* y, long long nrows
   if (h->generic) {
     if (nrows < 1) return CHZ_OK;
     const size_t smem = (size_t)2 * h->M * sizeof(float2);
-    static thread_local bool attr_set = false;
+    static thread_local bool attr_set_dev[kMaxDev] = {false};
+    bool& attr_set = attr_set_dev[h->device % kMaxDev];
     if (!attr_set) {
       CHZ_CUDA(cudaFuncSetAttribute(k_dft_rows_any, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * (int)sizeof(float2)));
       attr_set = true;
@@ -214,7 +219,8 @@ template <int P, bool IN16>
 static int launch_dit2(::chz* h, ChanParams prm, cudaStream_t st) {
   typedef Dit2Cfg<P> DC;
   auto kern = k_chan_dit2<P, IN16>;
-  static thread_local bool attr = false;
+  static thread_local bool attr_dev[kMaxDev] = {false};
+  bool& attr = attr_dev[h->device % kMaxDev];
   if (!attr) {
     CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DC::SMEM));
     attr = true;
@@ -244,7 +250,8 @@ template <int P, bool IN16>
 static int launch_ws(::chz* h, ChanParams prm, cudaStream_t st) {
   typedef WsCfg<64, P> WC;
   auto kern = k_chan_ws<64, P, IN16>;
-  static thread_local int blocks_per_sm = 0;
+  static thread_local int blocks_per_sm_dev[kMaxDev] = {0};   // launch geometry is cached per device
+  int& blocks_per_sm = blocks_per_sm_dev[h->device % kMaxDev];
   if (!blocks_per_sm) {
     CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WC::SMEM));
     int nb = 0;
@@ -278,7 +285,8 @@ static int launch_cluster(::chz* h, ChanParams prm, cudaStream_t st) {
     return 1;
   } else {
     auto kern = k_chan_cluster<M, P, IN16>;
-    static thread_local int nclusters = 0;
+    static thread_local int nclusters_dev[kMaxDev] = {0};
+    int& nclusters = nclusters_dev[h->device % kMaxDev];
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cudaLaunchAttribute attr[1];
