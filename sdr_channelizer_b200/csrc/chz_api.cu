@@ -336,6 +336,82 @@ static bool cluster_available(const ::chz* h) {
   return (h->P == 8 || h->P == 16) && h->P % C == 0;
 }
 
+// Pipelined split path (M = 1024, 2048, 4096): one persistent launch, FIR and in-place FFT tasks from one
+// ordered ticket queue (k_chan_pipe).  Returns 1 when there is no instantiation for (M, P).
+template <int M, int P, bool IN16>
+static int launch_pipe(::chz* h, ChanParams prm, cudaStream_t st) {
+  auto kern = k_chan_pipe<M, P, IN16>;
+  constexpr int ROWS = 4096 / M;
+  const size_t smem = (size_t)(2 * ROWS * RowStride<M>::value) * sizeof(float2);
+  static thread_local int blocks_per_sm_dev[kMaxDev] = {0};   // launch geometry is cached per device
+  int& blocks_per_sm = blocks_per_sm_dev[h->device % kMaxDev];
+  if (!blocks_per_sm) {
+    CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CHZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, smem));
+    blocks_per_sm = nb > 0 ? nb : 1;
+  }
+  long long max_blocks = (long long)h->sm_count * blocks_per_sm;
+  if (h->pipe_blocks > 0 && h->pipe_blocks < max_blocks) max_blocks = h->pipe_blocks;
+  // row groups: os * span_rows rows, span_rows a multiple of P near h->pipe_span_rows
+  long long sr = ((long long)h->pipe_span_rows + P - 1) / P * P;
+  if (sr < 2 * P) sr = 2 * P;
+  const long long rows_per_phase = (prm.nrows + prm.os - 1) / prm.os + 1;   // +1: a phase may start one row early
+  prm.span_rows = (int)sr;
+  prm.spans_per_phase = (rows_per_phase + sr - 1) / sr;
+  PipeParams pp;
+  memset(&pp, 0, sizeof pp);
+  const long long group_rows = (long long)prm.os * sr;
+  pp.ngroups_fir = (int)prm.spans_per_phase;
+  pp.ngroups_fft = (int)((prm.nrows + group_rows - 1) / group_rows);
+  pp.tpg = prm.os * (M / 256);
+  long long sub = 32768 / M;                      // ~32 Ki samples per FFT task, like a FIR task
+  if (sub < ROWS) sub = ROWS;
+  pp.sub_rows = (int)sub;
+  pp.tsub = (int)((group_rows + sub - 1) / sub);
+  const int slot_len = pp.tpg + pp.tsub;
+  // the FFT tasks of a group are drawn `lag` slots after its FIR tasks: a little more than the tickets the
+  // resident CTAs hold at any time, so the group is normally complete when its first FFT ticket is drawn
+  int lag = h->pipe_lag > 0 ? h->pipe_lag : (int)((max_blocks * 5 / 4 + slot_len - 1) / slot_len) + 2;
+  pp.lag = lag;
+  pp.need_next = 0;
+  for (int ph = 0; ph < prm.os; ph++) pp.need_next |= (int)(((prm.row_base + ph) / prm.os) & 1);
+  pp.total = (long long)(pp.ngroups_fir + lag) * slot_len;
+  const size_t ctrl_bytes = 16 + sizeof(int) * (size_t)(pp.ngroups_fir + 2);
+  CHZ_CUDA(h->pipe_ctrl.reserve(ctrl_bytes));
+  CHZ_CUDA(cudaMemsetAsync(h->pipe_ctrl.p, 0, ctrl_bytes, st));
+  pp.ticket = (unsigned long long*)h->pipe_ctrl.p;
+  pp.done = (int*)((char*)h->pipe_ctrl.p + 16);
+  long long blocks = pp.total < max_blocks ? pp.total : max_blocks;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, 256, smem, st>>>(prm, pp);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  return CHZ_OK;
+}
+
+template <bool IN16>
+static int launch_pipe_dispatch(::chz* h, const ChanParams& prm, cudaStream_t st) {
+#define CHZ_PIPE_P(MV)                                                 \
+  switch (h->P) {                                                      \
+    case 8: return launch_pipe<MV, 8, IN16>(h, prm, st);               \
+    case 12: return launch_pipe<MV, 12, IN16>(h, prm, st);             \
+    case 16: return launch_pipe<MV, 16, IN16>(h, prm, st);             \
+    default: return 1;                                                 \
+  }
+  switch (h->M) {
+    case 1024: CHZ_PIPE_P(1024)
+    case 2048: CHZ_PIPE_P(2048)
+    case 4096: CHZ_PIPE_P(4096)
+    default: return 1;
+  }
+#undef CHZ_PIPE_P
+}
+
+static bool pipe_available(const ::chz* h) {
+  return (h->M == 1024 || h->M == 2048 || h->M == 4096) && (h->P == 8 || h->P == 12 || h->P == 16);
+}
+
 static bool fused_available(const ::chz* h) {
   return !h->generic && h->M >= 8 && h->M <= 512 && (h->P == 8 || h->P == 12 || h->P == 16);
 }
@@ -377,7 +453,12 @@ static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, 
     if (h->force_path == 1 && !fused) return CHZ_EINVAL;
     const bool dit2 = dit2_available(h) && h->force_path == 5;
     if (h->force_path == 5 && !dit2) return CHZ_EINVAL;
-    if (dit2) {
+    const bool pipe = pipe_available(h) && h->force_path == 6;
+    if (h->force_path == 6 && !pipe) return CHZ_EINVAL;
+    if (pipe) {
+      rc = in16 ? launch_pipe_dispatch<true>(h, prm, st) : launch_pipe_dispatch<false>(h, prm, st);
+      if (rc) return rc == 1 ? CHZ_EINVAL : rc;
+    } else if (dit2) {
       rc = in16 ? launch_dit2_dispatch<true>(h, prm, st) : launch_dit2_dispatch<false>(h, prm, st);
       if (rc) return rc == 1 ? CHZ_EINVAL : rc;
     } else if (ws) {
@@ -592,6 +673,9 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
   CHZ_TRY(cudaMalloc(&h->d_tw, sizeof(float2) * M));
   CHZ_TRY(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
   if (const char* e = std::getenv("CHZ_SPLIT_OVERLAP")) h->split_overlap = std::atoi(e) != 0;   // tuning aid
+  if (const char* e = std::getenv("CHZ_PIPE_SPAN_ROWS")) { const int v = std::atoi(e); if (v > 0) h->pipe_span_rows = v; }   // tuning aids
+  if (const char* e = std::getenv("CHZ_PIPE_BLOCKS")) { const int v = std::atoi(e); if (v > 0) h->pipe_blocks = v; }
+  if (const char* e = std::getenv("CHZ_PIPE_LAG")) { const int v = std::atoi(e); if (v > 0) h->pipe_lag = v; }
   if (const char* e = std::getenv("CHZ_SPLIT_CHUNK_MB")) {   // tuning aid
     const long v = std::atol(e);
     if (v > 0) h->split_chunk_bytes = (uint64_t)v << 20;
@@ -623,6 +707,7 @@ void chz_destroy(chz_t* h) {
   if (h->d_store) cudaFree(h->d_store);
   if (h->d_u) cudaFree(h->d_u);
   h->cluster_ring.release();
+  h->pipe_ctrl.release();
   for (int i = 0; i < 4; i++) { if (h->ev_fir[i]) cudaEventDestroy(h->ev_fir[i]); if (h->ev_fft[i]) cudaEventDestroy(h->ev_fft[i]); }
   for (chzi::Scratch* sc : {&h->pdw_hist, &h->pdw_sel, &h->pdw_thr, &h->pdw_cnt, &h->pdw_ev, &h->pdw_pin, &h->pdw_pout}) sc->release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -653,7 +738,7 @@ int chz_set_option(chz_t* h, int opt, int64_t value) {
   switch (opt) {
     case CHZ_OPT_RETAIN: h->retain = value != 0; return CHZ_OK;
     case CHZ_OPT_CHUNK_ROWS: if (value < 0) return CHZ_EINVAL; h->chunk_rows = value; return CHZ_OK;
-    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 5) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
+    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 6) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
     default: return CHZ_EINVAL;
   }
 }

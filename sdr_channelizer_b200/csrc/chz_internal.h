@@ -68,6 +68,10 @@ struct chz {
   // cluster path: per-cluster L2-resident tile ring
   chzi::Scratch cluster_ring;
 
+  // pipelined split path: ticket + per-group completion counters, geometry knobs
+  chzi::Scratch pipe_ctrl;
+  int pipe_span_rows = 64, pipe_lag = 0, pipe_blocks = 0;
+
   // split-path scratch (FIR output rows)
   float2* d_u = nullptr;
   uint64_t u_cap_rows = 0;

@@ -660,4 +660,136 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) k_chan_dit2(
   cluster_barrier();   // do not exit while the partner may still read this CTA's shared memory
 }
 
+// ---- large M, pipelined split path: ONE persistent launch, FIR tasks and FFT tasks from one queue -----
+// The split path moves 4 + 8 + 8 + 8 B per sample through DRAM because a whole recording's FIR output
+// is written before the row FFT reads it back.  Here both stages run inside one launch and the FFT
+// trails the FIR by a few row groups, so the intermediate rows are still in the 126 MB L2 when they are
+// transformed in place: DRAM sees the raw input once and the final rows once (the fused kernel's
+// 4 + 8 B); the intermediate costs L2 bandwidth only.
+//   * the recording is cut into row groups of os*span_rows rows.  FIR task = (group, phase, pair of
+//     128-branch blocks): the register-window FIR of k_fir, two branch blocks side by side in a 256-thread
+//     CTA.  FFT task = SUB consecutive rows of a group: the body of k_fft_rows_big, in place.
+//   * tasks sit in ONE statically ordered queue: slot s = [FIR tasks of group s][FFT tasks of group s - lag].
+//     A CTA draws tickets with one atomicAdd (the next ticket is requested while the current task runs).
+//     An FFT task spins until the groups it reads are complete (per-group counters, release/acquire at gpu
+//     scope); `lag` is chosen so that this wait is normally over before the ticket is drawn.
+//   * deadlock-free without co-residency assumptions: a task only ever waits for tasks with smaller
+//     tickets, and every CTA works through its tickets in increasing order.
+// Arithmetic is exactly the split path's (same FIR pairs, same FFT plan): results are bit-identical.
+struct PipeParams {
+  unsigned long long* ticket;   // zeroed before the launch
+  int* done;                    // [ngroups_fir] finished FIR tasks per group, zeroed before the launch
+  int ngroups_fir;              // span groups (make_span's spans_per_phase)
+  int ngroups_fft;              // row groups of os*span_rows rows that contain at least one row
+  int lag;                      // slots between a group's FIR tasks and its FFT tasks
+  int tpg;                      // FIR tasks per group: os * M / 256
+  int tsub;                     // FFT tasks per group
+  int sub_rows;                 // rows per FFT task (multiple of the FFT tile height)
+  int need_next;                // a phase starts on an odd global row: group g's rows extend into span group g+1
+  long long total;              // tickets
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int M, int P, bool IN16>
+__global__ void __launch_bounds__(256, 2) k_chan_pipe(ChanParams prm, PipeParams pp) {
+  typedef Plan<M> PL;
+  static_assert(PL::np == 3 && PL::r0 == 16 && 4096 % M == 0, "large-M plan expected");
+  constexpr int ROWS = 4096 / M, S = RowStride<M>::value, BPR0 = M / 16, NBB2 = M / 256;
+  extern __shared__ float2 smem[];
+  __shared__ long long s_ticket;
+  float2* bufA = smem;
+  float2* bufB = bufA + ROWS * S;
+  const int t = threadIdx.x;
+  float2* const y = prm.out;
+  if (t == 0) s_ticket = (long long)atomicAdd(pp.ticket, 1ULL);
+  __syncthreads();
+  long long tk = s_ticket;
+  const int slot_len = pp.tpg + pp.tsub;
+  const long long group_rows = (long long)prm.os * prm.span_rows;
+  while (tk < pp.total) {
+    long long nxt = 0;
+    if (t == 0) nxt = (long long)atomicAdd(pp.ticket, 1ULL);   // used only after the task: latency hidden
+    const long long slot = tk / slot_len;
+    const int idx = (int)(tk - slot * slot_len);
+    if (idx < pp.tpg) {
+      // ---------------- FIR task: span group `slot`, phase idx / NBB2, branch blocks 2*(idx % NBB2) + {0,1}
+      if (slot < pp.ngroups_fir) {
+        const int phase = idx / NBB2, pair = idx - phase * NBB2;
+        const int p = (2 * pair + (t >> 7)) * 128 + (t & 127);
+        const Span sp = make_span(prm, slot * prm.os + phase);
+        if (sp.count > 0) {
+          const int r = (p - sp.shift + M) % M;          // u'[r] = u[(r + shift) mod M]
+          float2* dst = y + (sp.m0 - prm.row_base) * (long long)M + r;
+          const long long rstride = (long long)prm.os * M;
+          fir_span<P, IN16, M, 1>(prm, sp, p, [&](int, long long i, float2 v) {
+            if (i >= sp.skip && i < sp.count) dst[i * rstride] = v;
+          });
+        }
+        __syncthreads();                                 // every thread's rows are written ...
+        if (t == 0) {
+          __threadfence();                               // ... and ordered before the group's counter moves
+          atomicAdd(pp.done + slot, 1);
+        }
+      }
+    } else {
+      // ---------------- FFT task: rows [g*group_rows + j*sub_rows, + sub_rows) of the call, in place
+      const long long g = slot - pp.lag;
+      if (g >= 0 && g < pp.ngroups_fft) {
+        const int j = idx - pp.tpg;
+        const long long gbeg = g * group_rows;
+        long long r_begin = gbeg + (long long)j * pp.sub_rows;
+        long long r_end = r_begin + pp.sub_rows;
+        if (r_end > gbeg + group_rows) r_end = gbeg + group_rows;
+        if (r_end > prm.nrows) r_end = prm.nrows;
+        if (r_begin < r_end) {                           // block-uniform
+          if (t == 0) {
+            while (ld_acquire_gpu(pp.done + g) < pp.tpg) __nanosleep(64);
+            if (pp.need_next && g + 1 < pp.ngroups_fir)
+              while (ld_acquire_gpu(pp.done + g + 1) < pp.tpg) __nanosleep(64);
+          }
+          __syncthreads();
+          const int row = t / BPR0, jj = t % BPR0;
+          auto load = [&](long long r0, float2 (&v)[16]) {   // L2 loads: another SM wrote these rows
+            const bool ok = r0 + row < r_end;
+            const float2* src = y + (r0 + row) * (long long)M + jj;
+            #pragma unroll
+            for (int q = 0; q < 16; q++) v[q] = ok ? __ldcg(src + q * BPR0) : make_float2(0.f, 0.f);
+          };
+          float2 cur[16];
+          load(r_begin, cur);
+          for (long long r0 = r_begin; r0 < r_end; r0 += ROWS) {
+            float2 nx[16];
+            if (r0 + ROWS < r_end) load(r0 + ROWS, nx);
+            const long long left = r_end - r0;
+            const int vhi = (int)(left < ROWS ? left : ROWS);
+            dft<16>(cur);
+            {
+              float2* d = bufA + row * S;
+              #pragma unroll
+              for (int q = 0; q < 16; q++) d[padi<M>(jj * 16 + q)] = cur[q];
+            }
+            __syncthreads();
+            stockham_pass<M, PL::r1, PL::r0, ROWS, 256, false, false>(bufA, bufB, prm.tw, nullptr, t, nullptr, 0, 0, 0);
+            __syncthreads();
+            stockham_pass<M, PL::r2, PL::r0 * PL::r1, ROWS, 256, true, false>(bufB, bufA, prm.tw, nullptr, t,
+                                                                              y + r0 * (long long)M, (long long)M, 0, vhi);
+            #pragma unroll
+            for (int q = 0; q < 16; q++) cur[q] = nx[q];
+          }
+        }
+      }
+    }
+    __syncthreads();                                     // shared buffers and s_ticket are free again
+    if (t == 0) s_ticket = nxt;
+    __syncthreads();
+    tk = s_ticket;
+  }
+}
+
+
 }  // namespace chzi

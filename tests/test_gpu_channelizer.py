@@ -106,7 +106,8 @@ def test_channelizer_matches_oracle(orc, M, P, os_, kind, n):
                                           (512, 8, 2, 1), (32, 12, 2, 1), (128, 16, 1, 1), (16, 16, 1, 1),
                                           (64, 16, 1, 2), (1024, 16, 2, 0), (4096, 8, 1, 0), (64, 24, 1, 0), (64, 32, 2, 0),
                                           (4096, 16, 1, 3), (2048, 16, 2, 3), (1024, 8, 1, 3), (64, 16, 1, 4), (64, 16, 2, 4), (64, 12, 1, 4), (64, 8, 2, 4),
-                                          (1024, 16, 1, 5), (1024, 16, 2, 5), (1024, 12, 2, 5), (1024, 8, 1, 5)])
+                                          (1024, 16, 1, 5), (1024, 16, 2, 5), (1024, 12, 2, 5), (1024, 8, 1, 5),
+                                          (4096, 16, 1, 6), (2048, 16, 2, 6), (1024, 8, 1, 6), (1024, 12, 2, 6), (1024, 16, 2, 6), (2048, 12, 1, 6)])
 def test_random_taps_every_tap_index_matters(orc, M, P, os_, path):
     """A designed prototype has tiny end taps, which would hide a mis-indexed tap or window slot
     below the 1e-5 tolerance; with random taps of equal weight any such slip is an O(1/P) error."""
@@ -137,6 +138,36 @@ def test_split_path_equals_fused_path(M, P, os_):
         outs.append(ch(iq, bw))
         ch.close()
     assert synth.rel_rms(outs[0], outs[1]) < 1e-6
+
+
+@pytest.mark.parametrize("M,P,os_", [(1024, 16, 2), (1024, 16, 1), (2048, 12, 2), (4096, 16, 1), (4096, 8, 2)])
+def test_pipelined_path_is_bit_identical_to_split_path(M, P, os_):
+    """Path 6 (one persistent launch, FIR and in-place FFT tasks from one ticket queue) runs the split
+    path's arithmetic, so its rows must match bit for bit -- one shot and cut into ragged calls (odd row
+    counts move the pair alignment, so FFT tasks then depend on two span groups)."""
+    _torch()
+    n = M * 1500 // os_ + 13
+    iq, bw = synth.tones_int16_q11(n, M, seed=21)
+    taps = pkg.design_prototype(M, P)
+    ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=os_)
+    ch.set_option(_lib.CHZ_OPT_FORCE_PATH, 2)
+    whole = ch(iq, bw).copy()
+    ch.close()
+    ch = pkg.Channelizer(M, taps=taps, OversamplingRatio=os_)
+    ch.set_option(_lib.CHZ_OPT_FORCE_PATH, 6)
+    one = ch(iq, bw).copy()
+    assert np.array_equal(one.view(np.float32), whole.view(np.float32))
+    ch.reset()
+    D = M // os_
+    parts, pos = [], 0
+    for step in [D * 201 + 7, D * 3, 1, D * 333 + D // 2, D * 70, n]:
+        parts.append(ch(iq[pos:pos + step], bw).copy())
+        pos += step
+        if pos >= n:
+            break
+    got = np.concatenate(parts, axis=0)
+    assert got.shape == whole.shape and np.array_equal(got.view(np.float32), whole.view(np.float32))
+    ch.close()
 
 
 @pytest.mark.parametrize("M,P,os_", [(64, 16, 1), (32, 12, 2), (1024, 16, 2), (8, 8, 1)])
