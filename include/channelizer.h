@@ -191,6 +191,54 @@ int chz_pdws_fetch(const chz_t* h, chz_pdw_t* out, uint64_t cap, uint64_t* n);
 /* Per-channel noise floor (natural order, M doubles) of the last chz_pdws* call. */
 int chz_pdw_noise_floor(const chz_t* h, double* nf, uint32_t cap);
 
+/* ---- time-sharded PDW extraction (one shard of the recording per GPU) --------------------------
+ * create_pdws_channelized.m:73 takes the noise floor as the median over the WHOLE file, and a pulse may
+ * straddle a shard boundary, so the extractor is exposed in stages; the host (one process per GPU,
+ * sdr_channelizer_b200/sharding.py: create_pdws_sharded) runs them in lock-step and does the three small
+ * exchanges in between (NCCL through torch.distributed):
+ *   for pass = 0, 1, 2:  chz_pdw_shard_hist_dev -> all-reduce(sum) of the table -> chz_pdw_shard_select
+ *   chz_pdw_shard_thresholds                       (identical noise floor / thresholds on every rank)
+ *   chz_pdw_shard_exit_state_dev -> all-gather -> each rank folds the codes of the ranks before it
+ *   chz_pdw_shard_detect_dev(entry state)          (events carry rows of the whole recording)
+ *   all-gather events -> chz_pdw_pair_events       (same pulse list everywhere, reference order)
+ *   chz_pdw_shard_records_dev on the pulses inside the shard; for a pulse that straddles shards the
+ *   owner gathers the few column segments into a small matrix and calls it with ld = its width.
+ * Results are identical to chz_pdws_dev over the stitched matrix (tests). */
+typedef struct chz_pulse {
+  uint64_t toa_row, end_row;   /* 1-based rows of the leading / trailing edge in the whole recording  */
+  uint32_t channel_natural;    /* natural FFT-order channel of the pulse                              */
+  uint32_t col, col_phase;     /* columns of the matrix handed to chz_pdw_shard_records_dev holding    */
+                               /* the channel for |y| and for the phase (:114); = channel_natural when */
+                               /* that matrix is the channel matrix itself                             */
+  uint32_t reserved;
+} chz_pulse_t;
+
+/* Histogram of radix pass `pass` (0..2) over this shard's rows, accumulated into the handle's table
+ * (uint32 [M][2][2048], device memory, returned in *hist_dev; *hist_words = its length).  The call
+ * returns after the kernel has finished, so the table can be summed over ranks on any stream. */
+int chz_pdw_shard_hist_dev(chz_t* h, const chz_cf32* y_dev, uint64_t nrows, int pass, uint32_t** hist_dev, uint64_t* hist_words);
+/* Consume the (summed) table: fix the next bits of the two middle order statistics of `total_rows` values
+ * per channel, then clear the table for the next pass. */
+int chz_pdw_shard_select(chz_t* h, int pass, uint64_t total_rows);
+/* After pass 2: noise floor (chz_pdw_noise_floor) and thresholds (:73-75). */
+int chz_pdw_shard_thresholds(chz_t* h, const chz_pdw_params_t* params);
+/* code[k] (host, M bytes, natural channels): state of the edge FSM after this shard's last row as a
+ * function of the state it is entered with: 0 inactive, 1 active, 2 = entry state, 3 = entry state toggled. */
+int chz_pdw_shard_exit_state_dev(chz_t* h, const chz_cf32* y_dev, uint64_t nrows, uint8_t* code);
+/* Edge events of this shard.  entry: M bytes (host), FSM state per natural channel before the shard's
+ * first row (NULL = inactive, :83).  event = (shifted channel << 40) | (1-based row of the recording << 1)
+ * | (1 = trailing edge).  CHZ_ECAPACITY with *n = count when cap is too small. */
+int chz_pdw_shard_detect_dev(chz_t* h, const chz_cf32* y_dev, uint64_t nrows, uint64_t row_offset, const uint8_t* entry,
+                             uint64_t* events, uint64_t cap, uint64_t* n);
+/* Host only: sort the events of ALL shards and pair them into pulses in the reference's output order
+ * (shifted channel ascending, then time, :79,85); a pulse still open at the end is dropped (:135). */
+int chz_pdw_pair_events(uint64_t* events, uint64_t n, uint32_t M, uint32_t reproduce_phase_bug, chz_pulse_t* pulses,
+                        uint64_t cap, uint64_t* npulses);
+/* Records (:97-128) of pulses whose rows all lie inside y_dev: a row-major matrix with leading dimension
+ * ld whose first row is row row_offset + 1 of the recording. */
+int chz_pdw_shard_records_dev(chz_t* h, const chz_pdw_params_t* params, const chz_cf32* y_dev, uint64_t ld,
+                              uint64_t row_offset, const chz_pulse_t* pulses, uint64_t n, chz_pdw_t* out);
+
 /* Device pointer and row count of the retained store (for callers that keep working on the GPU). */
 int chz_retained(const chz_t* h, const chz_cf32** y_dev, uint64_t* nrows);
 int chz_reserve_rows(chz_t* h, uint64_t nrows);

@@ -23,6 +23,8 @@ EXPORTS = [
     "chz_unpack_dev", "chz_fft_rows_dev",
     "chz_pdws", "chz_pdws_dev", "chz_pdws_fetch", "chz_pdw_noise_floor", "chz_retained", "chz_reserve_rows",
     "chz_kernel_launches", "chz_alloc_host", "chz_free_host",
+    "chz_pdw_shard_hist_dev", "chz_pdw_shard_select", "chz_pdw_shard_thresholds", "chz_pdw_shard_exit_state_dev",
+    "chz_pdw_shard_detect_dev", "chz_pdw_pair_events", "chz_pdw_shard_records_dev",
 ]
 
 
@@ -49,6 +51,11 @@ class Pdw(C.Structure):
                 ("channel", C.c_uint32), ("channel_natural", C.c_uint32),
                 ("toa_row", C.c_uint64), ("end_row", C.c_uint64),
                 ("saturated", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Pulse(C.Structure):
+    _fields_ = [("toa_row", C.c_uint64), ("end_row", C.c_uint64), ("channel_natural", C.c_uint32),
+                ("col", C.c_uint32), ("col_phase", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class ChannelizerError(RuntimeError):
@@ -105,6 +112,13 @@ def lib():
     L.chz_retained.argtypes = [vp, C.POINTER(vp), pu64]; L.chz_retained.restype = i32
     L.chz_reserve_rows.argtypes = [vp, u64]; L.chz_reserve_rows.restype = i32
     L.chz_kernel_launches.argtypes = [vp]; L.chz_kernel_launches.restype = u64
+    L.chz_pdw_shard_hist_dev.argtypes = [vp, vp, u64, i32, C.POINTER(vp), pu64]; L.chz_pdw_shard_hist_dev.restype = i32
+    L.chz_pdw_shard_select.argtypes = [vp, i32, u64]; L.chz_pdw_shard_select.restype = i32
+    L.chz_pdw_shard_thresholds.argtypes = [vp, C.POINTER(PdwParams)]; L.chz_pdw_shard_thresholds.restype = i32
+    L.chz_pdw_shard_exit_state_dev.argtypes = [vp, vp, u64, vp]; L.chz_pdw_shard_exit_state_dev.restype = i32
+    L.chz_pdw_shard_detect_dev.argtypes = [vp, vp, u64, u64, vp, vp, u64, pu64]; L.chz_pdw_shard_detect_dev.restype = i32
+    L.chz_pdw_pair_events.argtypes = [vp, u64, u32, u32, vp, u64, pu64]; L.chz_pdw_pair_events.restype = i32
+    L.chz_pdw_shard_records_dev.argtypes = [vp, C.POINTER(PdwParams), vp, u64, u64, vp, u64, vp]; L.chz_pdw_shard_records_dev.restype = i32
     L.chz_alloc_host.argtypes = [u64]; L.chz_alloc_host.restype = vp
     L.chz_free_host.argtypes = [vp]; L.chz_free_host.restype = None
     _lib = L

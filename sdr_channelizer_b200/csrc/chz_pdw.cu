@@ -132,6 +132,7 @@ struct Thr { float ge, le; };
 // event = (shifted channel << 40) | (1-based row << 1) | (1 = trailing edge)
 __global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, long long nrows, int M,
                                                 const Thr* __restrict__ thr, int chunk_rows,
+                                                const uint8_t* __restrict__ entry, unsigned long long row_offset,
                                                 unsigned long long* __restrict__ events,
                                                 unsigned long long cap, unsigned long long* __restrict__ count) {
   const int lanes_ch = M < 32 ? M : 32;                   // channels per warp
@@ -157,8 +158,9 @@ __global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, lo
   // State on entry = state after row r0-1.  Walking back: a sample >= ge leaves the FSM active, one
   // <= le leaves it inactive whatever came before; samples strictly between the two thresholds
   // (hysteresis only) keep the earlier state; a sample exactly equal to a single representable threshold
-  // toggles it (:88 uses >=, :94 uses <= on the same value).
-  bool active = false;
+  // toggles it (:88 uses >=, :94 uses <= on the same value).  `entry` (time shards, per natural channel) is
+  // the state the previous shard left behind; NULL = the FSM starts inactive (:83).
+  bool active = entry ? entry[ch] != 0 : false;
   if (live && r0 > 0) {
     bool flips = false;
     for (long long j = r0 - 1; j >= 0; j--) {
@@ -193,11 +195,31 @@ __global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, lo
         base = __shfl_sync(0xffffffffu, base, 0);
         if (ev) {
           const unsigned long long slot = base + __popc(ball & ((1u << lane) - 1));
-          if (slot < cap) events[slot] = (chs << 40) | ((unsigned long long)(r + 1) << 1) | (active ? 0ull : 1ull);
+          if (slot < cap) events[slot] = (chs << 40) | (((unsigned long long)(r + 1) + row_offset) << 1) | (active ? 0ull : 1ull);
         }
       }
     }
   }
+}
+
+// State a shard leaves behind, per natural channel, as a function of the state it was entered with:
+// 0 = inactive, 1 = active (a decisive sample was found walking back from the last row), 2 = the entry
+// state, 3 = the entry state toggled (every sample sat between the thresholds or exactly on a single one).
+__global__ void __launch_bounds__(128) k_exit_state(const float2* __restrict__ y, long long nrows, int M,
+                                                    const Thr* __restrict__ thr, uint8_t* __restrict__ code) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= M) return;
+  const Thr t = thr[ch];
+  const bool exact = t.ge == t.le;
+  bool flips = false;
+  int c = 2;
+  for (long long j = nrows - 1; j >= 0; j--) {
+    const float m = mag_of(y[j * M + ch]);
+    if (exact && m == t.ge) { flips = !flips; continue; }
+    if (m >= t.ge) { c = 1; break; }
+    if (m <= t.le) { c = 0; break; }
+  }
+  code[ch] = (uint8_t)(c == 2 ? (flips ? 3 : 2) : (flips ? 1 - c : c));
 }
 
 // ---- per-pulse statistics ----------------------------------------------------------------------------
@@ -255,13 +277,16 @@ __device__ void block_select2(KeyF key, unsigned long long n, unsigned long long
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(128) k_pulse_stats(const float2* __restrict__ y, int M, double sat_level,
+// y is any row-major matrix with leading dimension M whose row 0 is (1-based) row row0 + 1 of the run;
+// p.k / p.kph are COLUMNS of that matrix.
+__global__ void __launch_bounds__(128) k_pulse_stats(const float2* __restrict__ y, long long M, double sat_level,
+                                                     unsigned long long row0,
                                                      const PulseIn* __restrict__ in, PulseOut* __restrict__ outp) {
   __shared__ uint32_t h0[256], h1[256], res[2];
   __shared__ unsigned long long sh_rank[2];
   __shared__ int sh_sat;
   const PulseIn p = in[blockIdx.x];
-  const unsigned long long a = p.toa - 1, b = p.end - 1;   // 0-based inclusive rows
+  const unsigned long long a = p.toa - 1 - row0, b = p.end - 1 - row0;   // 0-based inclusive rows of y
   if (threadIdx.x == 0) sh_sat = 0;
   __syncthreads();
   // saturation: rows strictly between the edges (:129-132 runs only while the pulse stays active)
@@ -289,51 +314,58 @@ __global__ void __launch_bounds__(128) k_pulse_stats(const float2* __restrict__ 
 }
 
 // ---- host driver ---------------------------------------------------------------------------------------
-int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t nrows) {
+// Stages shared by the one-GPU extractor (pdw_extract) and the time-sharded one (chz_pdw_shard_*, where
+// the host sums the histograms of all shards between hist and select).
+static int pdw_buffers(::chz* h) {
   const int M = (int)h->M;
-  cudaStream_t st = h->stream;
-  // CHZ_PDW_TRACE=1: host wall-clock of each stage on stderr (debug aid)
-  static const bool trace = std::getenv("CHZ_PDW_TRACE") != nullptr;
-  auto t_prev = std::chrono::steady_clock::now();
-  auto lap = [&](const char* what) {
-    if (!trace) return;
-    const auto now = std::chrono::steady_clock::now();
-    std::fprintf(stderr, "[chz pdw] %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
-    t_prev = now;
-  };
-  h->pdws.clear();
-  h->noise_floor.assign(M, NAN);
-  if (nrows == 0) return CHZ_OK;
-
-  // 1. exact per-channel median of |y| (:73)
+  const bool fresh = h->pdw_hist.bytes < (size_t)M * 2 * kBins * sizeof(uint32_t);
   CHZ_CUDA(h->pdw_hist.reserve((size_t)M * 2 * kBins * sizeof(uint32_t)));
   CHZ_CUDA(h->pdw_sel.reserve((size_t)M * sizeof(SelState)));
   CHZ_CUDA(h->pdw_thr.reserve((size_t)M * sizeof(Thr)));
   CHZ_CUDA(h->pdw_cnt.reserve(sizeof(unsigned long long)));
+  CHZ_CUDA(h->pdw_code.reserve((size_t)M));
+  (void)fresh;
+  return CHZ_OK;
+}
+
+// local histogram of one radix pass (:73); pass 0 clears the table first (k_select clears it after every pass)
+static int pdw_hist_pass(::chz* h, const float2* y, uint64_t nrows, int pass) {
+  const int M = (int)h->M;
+  cudaStream_t st = h->stream;
+  int rc = pdw_buffers(h);
+  if (rc) return rc;
   uint32_t* d_hist = (uint32_t*)h->pdw_hist.p;
-  SelState* d_sel = (SelState*)h->pdw_sel.p;
-  Thr* d_thr = (Thr*)h->pdw_thr.p;
-  unsigned long long* d_cnt = (unsigned long long*)h->pdw_cnt.p;
-  CHZ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)M * 2 * kBins * sizeof(uint32_t), st));
-  lap("alloc");
-  const uint32_t rank_lo = (uint32_t)((nrows - 1) / 2), rank_hi = (uint32_t)(nrows / 2);
+  if (pass == 0) CHZ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)M * 2 * kBins * sizeof(uint32_t), st));
+  if (nrows == 0) return CHZ_OK;
   long long ychunks = (h->sm_count * 4 + (M + 3) / 4 - 1) / ((M + 3) / 4);
   const long long max_chunks = (long long)((nrows + 255) / 256);
   if (ychunks > max_chunks) ychunks = max_chunks;
   if (ychunks < 1) ychunks = 1;
   if (ychunks > 65535) ychunks = 65535;
-  for (int pass = 0; pass < 3; pass++) {
-    k_hist<<<dim3((M + 3) / 4, (unsigned)ychunks), 256, 0, st>>>(y, (long long)nrows, M, pass, d_sel, d_hist);
-    k_select<<<M, 256, 0, st>>>(d_hist, d_sel, pass, rank_lo, rank_hi);
-    h->launches += 2;
-  }
+  k_hist<<<dim3((M + 3) / 4, (unsigned)ychunks), 256, 0, st>>>(y, (long long)nrows, M, pass, (const SelState*)h->pdw_sel.p, d_hist);
+  h->launches++;
   CHZ_CUDA(cudaGetLastError());
-  std::vector<SelState> sel(M);
-  CHZ_CUDA(cudaMemcpyAsync(sel.data(), d_sel, sizeof(SelState) * M, cudaMemcpyDeviceToHost, st));
-  CHZ_CUDA(cudaStreamSynchronize(st));
+  return CHZ_OK;
+}
 
-  lap("median");
-  // 2. thresholds (:74-75), double on the host, bracketed by floats for the fp32 comparisons
+// fix the next bits of both middle order statistics from the (summed) histogram; total_rows = rows of the
+// WHOLE recording
+static int pdw_select_pass(::chz* h, int pass, uint64_t total_rows) {
+  if (total_rows == 0 || total_rows > 0xFFFFFFFFull) return CHZ_EINVAL;
+  const uint32_t rank_lo = (uint32_t)((total_rows - 1) / 2), rank_hi = (uint32_t)(total_rows / 2);
+  k_select<<<h->M, 256, 0, h->stream>>>((uint32_t*)h->pdw_hist.p, (SelState*)h->pdw_sel.p, pass, rank_lo, rank_hi);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  return CHZ_OK;
+}
+
+// noise floor and thresholds (:73-75), double on the host, bracketed by floats for the fp32 comparisons
+static int pdw_thresholds(::chz* h, const chz_pdw_params_t* prm) {
+  const int M = (int)h->M;
+  cudaStream_t st = h->stream;
+  std::vector<SelState> sel(M);
+  CHZ_CUDA(cudaMemcpyAsync(sel.data(), h->pdw_sel.p, sizeof(SelState) * M, cudaMemcpyDeviceToHost, st));
+  CHZ_CUDA(cudaStreamSynchronize(st));
   const double scale = std::pow(10.0, prm->snr_threshold_db / 10.0);
   // create_pdws.m:47: TRAILING_EDGE_THRESHOLD = NOISE_FLOOR*10^(3/10); never above the leading threshold
   const bool hyst = prm->use_trailing_threshold != 0 && prm->trailing_snr_threshold_db < prm->snr_threshold_db;
@@ -341,6 +373,7 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
   auto float_ge = [](double t) { float f = (float)t; return (double)f < t ? std::nextafterf(f, INFINITY) : f; };
   auto float_le = [](double t) { float f = (float)t; return (double)f > t ? std::nextafterf(f, -INFINITY) : f; };
   std::vector<Thr> thr(M);
+  h->noise_floor.assign(M, NAN);
   for (int k = 0; k < M; k++) {
     float lo, hi;
     memcpy(&lo, &sel[k].prefix[0], 4);
@@ -350,22 +383,38 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
     thr[k].ge = float_ge(nf * scale);
     thr[k].le = float_le(nf * scale_lo);
   }
-  CHZ_CUDA(cudaMemcpyAsync(d_thr, thr.data(), sizeof(Thr) * M, cudaMemcpyHostToDevice, st));
+  CHZ_CUDA(cudaMemcpyAsync(h->pdw_thr.p, thr.data(), sizeof(Thr) * M, cudaMemcpyHostToDevice, st));
+  CHZ_CUDA(cudaStreamSynchronize(st));   // thr lives on this stack frame
+  return CHZ_OK;
+}
 
-  // 3. edge events (:79-96)
+// edge events (:79-96) of y[nrows][M]; rows in the events are 1-based and offset by row_offset;
+// entry_host: per natural channel state on entry (NULL = inactive)
+static int pdw_detect(::chz* h, const float2* y, uint64_t nrows, uint64_t row_offset, const uint8_t* entry_host,
+                      std::vector<unsigned long long>& ev) {
+  const int M = (int)h->M;
+  cudaStream_t st = h->stream;
+  ev.clear();
+  if (nrows == 0) return CHZ_OK;
+  unsigned long long* d_cnt = (unsigned long long*)h->pdw_cnt.p;
+  uint8_t* d_entry = nullptr;
+  if (entry_host) {
+    d_entry = (uint8_t*)h->pdw_code.p;
+    CHZ_CUDA(cudaMemcpyAsync(d_entry, entry_host, (size_t)M, cudaMemcpyHostToDevice, st));
+  }
   const int chunk_rows = 64;
   const long long nchunks = ((long long)nrows + chunk_rows - 1) / chunk_rows;
   const int lanes_ch = M < 32 ? M : 32, streams = 32 / lanes_ch, ch_groups = (M + 31) / 32;
   const long long warps = ((nchunks + streams - 1) / streams) * ch_groups;
   const long long blocks = (warps + 7) / 8;
   unsigned long long nev = 0;
-  std::vector<unsigned long long> ev;
   for (;;) {
     const unsigned long long cap = h->pdw_ev_cap;
     CHZ_CUDA(h->pdw_ev.reserve(cap * sizeof(unsigned long long)));
     unsigned long long* d_ev = (unsigned long long*)h->pdw_ev.p;
     CHZ_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
-    k_detect<<<(unsigned)blocks, 256, 0, st>>>(y, (long long)nrows, M, d_thr, chunk_rows, d_ev, cap, d_cnt);
+    k_detect<<<(unsigned)blocks, 256, 0, st>>>(y, (long long)nrows, M, (const Thr*)h->pdw_thr.p, chunk_rows, d_entry,
+                                               (unsigned long long)row_offset, d_ev, cap, d_cnt);
     h->launches++;
     CHZ_CUDA(cudaGetLastError());
     CHZ_CUDA(cudaMemcpyAsync(&nev, d_cnt, sizeof nev, cudaMemcpyDeviceToHost, st));
@@ -380,64 +429,200 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
     }
     h->pdw_ev_cap = nev + nev / 4;   // rerun with room for everything
   }
-  lap("detect");
-  // 4. pair edges per channel in time order; a pulse still open at the end is dropped (:135)
+  return CHZ_OK;
+}
+
+// pair edges per channel in time order (sorts ev); a pulse still open at the end is dropped (:135)
+static void pdw_pair(std::vector<unsigned long long>& ev, uint32_t M, bool phase_bug, std::vector<chz_pulse_t>& pulses) {
   std::sort(ev.begin(), ev.end());
-  std::vector<PulseIn> pulses;
+  pulses.clear();
   const uint32_t kbug = (uint32_t)((0 + (M + 1) / 2) % M);   // natural channel of shifted column 1 (:114)
   for (size_t i = 0; i + 1 < ev.size(); i++) {
     const unsigned long long e0 = ev[i], e1 = ev[i + 1];
     if ((e0 & 1ull) == 0 && (e1 & 1ull) == 1 && (e0 >> 40) == (e1 >> 40)) {
-      PulseIn p;
-      p.toa = (e0 & ((1ull << 40) - 1)) >> 1;
-      p.end = (e1 & ((1ull << 40) - 1)) >> 1;
+      chz_pulse_t p;
+      memset(&p, 0, sizeof p);
+      p.toa_row = (e0 & ((1ull << 40) - 1)) >> 1;
+      p.end_row = (e1 & ((1ull << 40) - 1)) >> 1;
       const uint32_t c = (uint32_t)(e0 >> 40);
-      p.k = (c + (uint32_t)(M + 1) / 2) % (uint32_t)M;
-      p.kph = prm->reproduce_phase_bug ? kbug : p.k;
+      p.channel_natural = (c + (M + 1) / 2) % M;
+      p.col = p.channel_natural;
+      p.col_phase = phase_bug ? kbug : p.channel_natural;
       pulses.push_back(p);
       i++;
     }
   }
-  if (pulses.empty()) return CHZ_OK;
+}
 
-  lap("pair");
-  // 5. per-pulse medians and saturation (:97-122)
-  CHZ_CUDA(h->pdw_pin.reserve(pulses.size() * sizeof(PulseIn)));
-  CHZ_CUDA(h->pdw_pout.reserve(pulses.size() * sizeof(PulseOut)));
+// per-pulse medians and saturation (:97-122) and the records (:97-128) for pulses whose rows all lie in
+// y (leading dimension ld, row 0 = 1-based row row_offset + 1 of the run; columns p.col / p.col_phase)
+static int pdw_records(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t ld, uint64_t row_offset,
+                       const chz_pulse_t* pulses, size_t n, chz_pdw_t* out) {
+  if (n == 0) return CHZ_OK;
+  if (h->noise_floor.size() != h->M) return CHZ_ESTATE;
+  const int M = (int)h->M;
+  cudaStream_t st = h->stream;
+  std::vector<PulseIn> pin(n);
+  for (size_t i = 0; i < n; i++) {
+    pin[i].toa = pulses[i].toa_row; pin[i].end = pulses[i].end_row;
+    pin[i].k = pulses[i].col; pin[i].kph = pulses[i].col_phase;
+    if (pin[i].toa <= row_offset || pin[i].end < pin[i].toa || pin[i].k >= ld || pin[i].kph >= ld) return CHZ_EINVAL;
+  }
+  CHZ_CUDA(h->pdw_pin.reserve(n * sizeof(PulseIn)));
+  CHZ_CUDA(h->pdw_pout.reserve(n * sizeof(PulseOut)));
   PulseIn* d_pin = (PulseIn*)h->pdw_pin.p;
   PulseOut* d_pout = (PulseOut*)h->pdw_pout.p;
-  CHZ_CUDA(cudaMemcpyAsync(d_pin, pulses.data(), pulses.size() * sizeof(PulseIn), cudaMemcpyHostToDevice, st));
-  k_pulse_stats<<<(unsigned)pulses.size(), 128, 0, st>>>(y, M, prm->sat_level, d_pin, d_pout);
+  CHZ_CUDA(cudaMemcpyAsync(d_pin, pin.data(), n * sizeof(PulseIn), cudaMemcpyHostToDevice, st));
+  k_pulse_stats<<<(unsigned)n, 128, 0, st>>>(y, (long long)ld, prm->sat_level, (unsigned long long)row_offset, d_pin, d_pout);
   h->launches++;
   CHZ_CUDA(cudaGetLastError());
-  std::vector<PulseOut> pout(pulses.size());
-  CHZ_CUDA(cudaMemcpyAsync(pout.data(), d_pout, pulses.size() * sizeof(PulseOut), cudaMemcpyDeviceToHost, st));
+  std::vector<PulseOut> pout(n);
+  CHZ_CUDA(cudaMemcpyAsync(pout.data(), d_pout, n * sizeof(PulseOut), cudaMemcpyDeviceToHost, st));
   CHZ_CUDA(cudaStreamSynchronize(st));
-
-  lap("stats");
-  // 6. records (:97-128), already in the reference's order: shifted channel ascending, then time
+  // records (:97-128)
   const double fs_dec = prm->fs_sps / (double)h->D;        // :62
-  h->pdws.resize(pulses.size());
-  for (size_t i = 0; i < pulses.size(); i++) {
-    const PulseIn& p = pulses[i];
+  for (size_t i = 0; i < n; i++) {
+    const chz_pulse_t& p = pulses[i];
     const PulseOut& o = pout[i];
     chz_pdw_t r;
     memset(&r, 0, sizeof r);
-    const uint32_t c = (p.k + (uint32_t)(M / 2)) % (uint32_t)M;
+    const uint32_t k = p.channel_natural;
+    const uint32_t c = (k + (uint32_t)(M / 2)) % (uint32_t)M;
     const double bin_freq = ((double)c - (double)(M / 2)) * prm->fs_sps / (double)M;   // :42 on shifted columns
-    const double nf = h->noise_floor[p.k];
+    const double nf = h->noise_floor[k];
     const double med_pd = 0.5 * ((double)o.pd_lo + (double)o.pd_hi);
-    r.toa_s = ((double)p.toa / fs_dec) + prm->t0;                                       // :98
+    r.toa_s = ((double)p.toa_row / fs_dec) + prm->t0;                                   // :98
     r.amp = 0.5 * ((double)o.amp_lo + (double)o.amp_hi);                                // :101
     r.snr_db = 10.0 * std::log10(r.amp / nf);                                           // :105
-    r.pw_s = (double)(p.end - p.toa) / fs_dec;                                          // :110
+    r.pw_s = (double)(p.end_row - p.toa_row) / fs_dec;                                  // :110
     r.freq_hz = (prm->fc_hz + bin_freq) + (fs_dec / (360.0 / med_pd));                  // :80, :122
     r.noise_floor = nf;
-    r.channel = c; r.channel_natural = p.k;
-    r.toa_row = p.toa; r.end_row = p.end; r.saturated = o.sat;
-    h->pdws[i] = r;
+    r.channel = c; r.channel_natural = k;
+    r.toa_row = p.toa_row; r.end_row = p.end_row; r.saturated = o.sat;
+    out[i] = r;
   }
   return CHZ_OK;
 }
 
+int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t nrows) {
+  const int M = (int)h->M;
+  // CHZ_PDW_TRACE=1: host wall-clock of each stage on stderr (debug aid)
+  static const bool trace = std::getenv("CHZ_PDW_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[chz pdw] %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
+  h->pdws.clear();
+  h->noise_floor.assign(M, NAN);
+  if (nrows == 0) return CHZ_OK;
+  int rc;
+  // 1. exact per-channel median of |y| (:73)
+  for (int pass = 0; pass < 3; pass++) {
+    if ((rc = pdw_hist_pass(h, y, nrows, pass))) return rc;
+    if ((rc = pdw_select_pass(h, pass, nrows))) return rc;
+  }
+  lap("median");
+  // 2. thresholds (:74-75)
+  if ((rc = pdw_thresholds(h, prm))) return rc;
+  // 3. edge events (:79-96)
+  std::vector<unsigned long long> ev;
+  if ((rc = pdw_detect(h, y, nrows, 0, nullptr, ev))) return rc;
+  lap("detect");
+  // 4. pulses in the reference's order: shifted channel ascending, then time
+  std::vector<chz_pulse_t> pulses;
+  pdw_pair(ev, (uint32_t)M, prm->reproduce_phase_bug != 0, pulses);
+  lap("pair");
+  if (pulses.empty()) return CHZ_OK;
+  // 5./6. per-pulse statistics and records
+  h->pdws.resize(pulses.size());
+  rc = pdw_records(h, prm, y, (uint64_t)M, 0, pulses.data(), pulses.size(), h->pdws.data());
+  if (rc) h->pdws.clear();
+  lap("stats");
+  return rc;
+}
+
 }  // namespace chzi
+
+using namespace chzi;
+
+// ---- time-sharded PDW extraction: the stages above, one shard per GPU --------------------
+extern "C" {
+
+int chz_pdw_shard_hist_dev(chz_t* h, const chz_cf32* y_dev, uint64_t nrows, int pass, uint32_t** hist_dev, uint64_t* hist_words) {
+  if (!h || (!y_dev && nrows) || pass < 0 || pass > 2) return CHZ_EINVAL;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  const int rc = pdw_hist_pass(h, (const float2*)y_dev, nrows, pass);
+  if (rc) return rc;
+  CHZ_CUDA(cudaStreamSynchronize(h->stream));   // the caller sums the table on its own stream / communicator
+  if (hist_dev) *hist_dev = (uint32_t*)h->pdw_hist.p;
+  if (hist_words) *hist_words = (uint64_t)h->M * 2 * kBins;
+  return CHZ_OK;
+}
+
+int chz_pdw_shard_select(chz_t* h, int pass, uint64_t total_rows) {
+  if (!h || pass < 0 || pass > 2 || !h->pdw_hist.p) return CHZ_EINVAL;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  const int rc = pdw_select_pass(h, pass, total_rows);
+  if (rc) return rc;
+  CHZ_CUDA(cudaStreamSynchronize(h->stream));
+  return CHZ_OK;
+}
+
+int chz_pdw_shard_thresholds(chz_t* h, const chz_pdw_params_t* params) {
+  if (!h || !params || !h->pdw_sel.p) return CHZ_EINVAL;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  h->pdws.clear();
+  return pdw_thresholds(h, params);
+}
+
+int chz_pdw_shard_exit_state_dev(chz_t* h, const chz_cf32* y_dev, uint64_t nrows, uint8_t* code) {
+  if (!h || !code || (!y_dev && nrows)) return CHZ_EINVAL;
+  if (h->noise_floor.size() != h->M) return CHZ_ESTATE;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  k_exit_state<<<(h->M + 127) / 128, 128, 0, h->stream>>>((const float2*)y_dev, (long long)nrows, (int)h->M,
+                                                           (const Thr*)h->pdw_thr.p, (uint8_t*)h->pdw_code.p);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  CHZ_CUDA(cudaMemcpyAsync(code, h->pdw_code.p, h->M, cudaMemcpyDeviceToHost, h->stream));
+  CHZ_CUDA(cudaStreamSynchronize(h->stream));
+  return CHZ_OK;
+}
+
+int chz_pdw_shard_detect_dev(chz_t* h, const chz_cf32* y_dev, uint64_t nrows, uint64_t row_offset, const uint8_t* entry,
+                             uint64_t* events, uint64_t cap, uint64_t* n) {
+  if (!h || !n || (!y_dev && nrows)) return CHZ_EINVAL;
+  if (h->noise_floor.size() != h->M) return CHZ_ESTATE;
+  if (row_offset + nrows >= (1ull << 39)) return CHZ_EINVAL;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  std::vector<unsigned long long> ev;
+  const int rc = pdw_detect(h, (const float2*)y_dev, nrows, row_offset, entry, ev);
+  if (rc) return rc;
+  *n = ev.size();
+  if (ev.size() > cap) return CHZ_ECAPACITY;
+  if (events && !ev.empty()) memcpy(events, ev.data(), ev.size() * sizeof(uint64_t));
+  return CHZ_OK;
+}
+
+int chz_pdw_pair_events(uint64_t* events, uint64_t n, uint32_t M, uint32_t reproduce_phase_bug, chz_pulse_t* pulses,
+                        uint64_t cap, uint64_t* npulses) {
+  if ((!events && n) || !npulses || M == 0) return CHZ_EINVAL;
+  std::vector<unsigned long long> ev(events, events + n);
+  std::vector<chz_pulse_t> p;
+  pdw_pair(ev, M, reproduce_phase_bug != 0, p);
+  *npulses = p.size();
+  if (p.size() > cap) return CHZ_ECAPACITY;
+  if (pulses && !p.empty()) memcpy(pulses, p.data(), p.size() * sizeof(chz_pulse_t));
+  return CHZ_OK;
+}
+
+int chz_pdw_shard_records_dev(chz_t* h, const chz_pdw_params_t* params, const chz_cf32* y_dev, uint64_t ld,
+                              uint64_t row_offset, const chz_pulse_t* pulses, uint64_t n, chz_pdw_t* out) {
+  if (!h || !params || ((!y_dev || !pulses || !out) && n) || ld == 0) return CHZ_EINVAL;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  return pdw_records(h, params, (const float2*)y_dev, ld, row_offset, pulses, (size_t)n, out);
+}
+
+}  // extern "C"

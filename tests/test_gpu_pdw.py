@@ -174,3 +174,91 @@ def test_wideband_create_pdws_script(orc, tmp_path):
     t[500:600] = 0.9; t[600:650] = 0.05; t[650] = 0.0101; t[900:905] = 0.8
     recs, _ = _pdws_on_matrix(t.reshape(-1, 1), 1e6, SNR_THRESHOLD=18.0, TRAILING_EDGE_THRESHOLD=3.0)
     assert [(r.toa_row, r.end_row) for r in recs] == [(501, 651), (901, 906)]
+
+
+# ---- time-sharded extraction: distributed median + boundary stitching ---------------------
+def _sharded_on_one_gpu(y, bounds, fs, **kw):
+    """create_pdws_sharded with one thread per shard (each with its own handle and stream) on one GPU;
+    the exchanges go through ThreadComm instead of NCCL, everything else is the multi-GPU code path."""
+    import threading
+    torch = _torch()
+    from sdr_channelizer_b200.sharding import PdwShard, ThreadComm, create_pdws_sharded
+    M = y.shape[1]
+    d = torch.from_numpy(np.ascontiguousarray(y.astype(np.complex64))).cuda()
+    torch.cuda.synchronize()
+    world = len(bounds) - 1
+    comms = ThreadComm.make(world)
+    results, errors = [None] * world, []
+
+    def run(r):
+        try:
+            ch = pkg.Channelizer(M, NumTapsPerBand=8) if M > 1 else pkg.Channelizer(1, taps=np.ones(1, np.float32))
+            a, b = bounds[r], bounds[r + 1]
+            shard = PdwShard(ch, d.data_ptr() + a * M * 8, b - a, a, y.shape[0], fs, **kw)
+            results[r] = create_pdws_sharded(shard, comms[r])
+            ch.close()
+        except Exception as e:   # surface the failure instead of dead-locking the other threads' barriers
+            errors.append(e)
+            comms[r]._sh["barrier"].abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    return results
+
+
+def _same_records(a, b):
+    assert len(a) == len(b)
+    for x, z in zip(a, b):
+        assert bytes(x) == bytes(z), ((x.toa_row, x.end_row, x.channel, x.amp, x.freq_hz), (z.toa_row, z.end_row, z.channel, z.amp, z.freq_hz))
+
+
+@pytest.mark.parametrize("bounds", [[0, 200, 400, 600], [0, 199, 600], [0, 1, 2, 600], [0, 64, 128, 192, 256, 320, 384, 600]])
+def test_sharded_pdws_identical_to_one_gpu(bounds):
+    """Every boundary case (tests/test_sharding.py::_pdw_matrix): records and noise floor of the sharded
+    extractor are byte-identical to chz_pdws_dev on the whole matrix, on every rank."""
+    from tests.test_sharding import _pdw_matrix
+    y = _pdw_matrix()
+    kw = dict(fc=1e9, sampleStartTime=3.0)
+    whole, nf = _pdws_on_matrix(y, 8e6, **kw)
+    assert len(whole) == 7
+    for recs, nfs in _sharded_on_one_gpu(y, bounds, 8e6, **kw):
+        _same_records(recs, whole)
+        assert np.array_equal(nfs, nf)
+
+
+def test_sharded_pdws_equality_toggle_across_boundaries():
+    """Threshold exactly representable (0 dB over a median of 2^-6): samples equal to it toggle the FSM
+    (:88,:94), so a shard's exit state is 'entry toggled n times' and must be folded across shards."""
+    M, rows = 8, 301
+    y = np.full((rows, M), 2.0 ** -6, dtype=np.complex64)
+    y[10:40, 1] = 0.5; y[100:230, 2] = 0.25; y[::2, 3] = 0.001; y[5, 4] = 0.7
+    whole, nf = _pdws_on_matrix(y, 8e6, SNR_THRESHOLD=0.0)
+    assert len(whole) > 100
+    for bounds in ([0, 100, 200, 301], [0, 151, 301], [0, 7, 301]):
+        for recs, nfs in _sharded_on_one_gpu(y, bounds, 8e6, SNR_THRESHOLD=0.0):
+            _same_records(recs, whole)
+
+
+def test_sharded_pdws_pulsed_recording_and_phase_bug():
+    """configs[4]-style pulsed recording through the channelizer, then the sharded extractor on 4 shards with
+    the :114 column-1 phase bug reproduced (boundary pulses then need two columns)."""
+    torch = _torch()
+    M, P = 64, 12
+    n = M * 40000
+    iq, bw, fs = synth.pulsed_int16(n, M=M, seed=7)
+    ch = pkg.Channelizer(M, taps=pkg.design_prototype(M, P))
+    y = ch(iq, bw)
+    ch.close()
+    rows = y.shape[0]
+    for bug in (False, True):
+        kw = dict(fc=2.4e9, sampleStartTime=10.0, reproduce_phase_bug=bug)
+        whole, nf = _pdws_on_matrix(y, fs, **kw)
+        assert len(whole) > 3
+        # put one boundary in the middle of the first pulse so at least one pulse straddles
+        mid = int(whole[0].toa_row + whole[0].end_row) // 2
+        bounds = sorted({0, mid, rows // 2, 3 * rows // 4, rows})
+        for recs, nfs in _sharded_on_one_gpu(y, bounds, fs, **kw):
+            _same_records(recs, whole)
+            assert np.array_equal(nfs, nf)

@@ -98,3 +98,65 @@ def test_gather_rows_in_time_order_gloo(tmp_path):
         g = torch.Generator().manual_seed(r)
         expect.append(torch.complex(torch.randn(n, 8, generator=g), torch.randn(n, 8, generator=g)))
     assert torch.equal(full, torch.cat(expect))
+
+
+# ---- PDW extraction over time shards: distributed median + boundary stitching -------------
+def _pdw_matrix(rows=600, M=8, seed=5):
+    """A channel matrix with pulses placed to exercise every boundary case of a 3-way row split
+    (200 rows each): inside one shard, straddling one boundary, spanning a whole shard, ending exactly
+    on a shard's last row, starting on a shard's first row, and open at the end (dropped, :135)."""
+    rng = np.random.default_rng(seed)
+    y = (rng.normal(size=(rows, M)) + 1j * rng.normal(size=(rows, M))) * 0.01
+    def pulse(k, a, b, f=0.05, amp=1.0):
+        n = np.arange(b - a)
+        y[a:b, k] += amp * np.exp(2j * np.pi * f * n)
+    pulse(0, 20, 60)
+    pulse(1, 150, 260, f=-0.11)            # straddles boundary 200
+    pulse(2, 180, 450, f=0.2, amp=0.95)    # spans the whole middle shard
+    pulse(3, 100, 200)                     # last pulse sample is the last row of shard 0
+    pulse(4, 200, 230)                     # first pulse sample is the first row of shard 1
+    pulse(5, 390, 410); pulse(5, 30, 50)   # two pulses in one channel, one straddling boundary 400
+    pulse(6, 580, 600)                     # still open at the end of the recording
+    return y.astype(np.complex64)
+
+
+def _pdw_worker(rank, world, port, y, bounds, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sdr_channelizer_b200.sharding import TorchDistComm, create_pdws_sharded
+    from tests.fake_pdw_shard import FakePdwShard
+    a, b = bounds[rank], bounds[rank + 1]
+    shard = FakePdwShard(y[a:b], a, y.shape[0], D=8, fs=8e6, fc=1e9, t0=3.0)
+    recs, nf = create_pdws_sharded(shard, TorchDistComm())
+    if rank == world - 1:
+        np.save(out_path, np.array([[r.toa_row, r.end_row, r.channel, r.amp, r.freq_hz, r.snr_db, r.toa_s, r.pw_s, r.saturated]
+                                    for r in recs] + [list(nf) + [0.0]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bounds", [[0, 200, 400, 600], [0, 600], [0, 199, 600], [0, 1, 2, 600]])
+def test_sharded_pdws_gloo_equal_the_oracle_on_the_stitched_matrix(tmp_path, orc, bounds):
+    """World-size 1..3 gloo runs of create_pdws_sharded (numpy stand-in for the GPU stages) against the
+    oracle's create_pdws_channelized.m restatement on the whole matrix: same pulses, same order, same rows."""
+    y = _pdw_matrix()
+    world = len(bounds) - 1
+    out_path = str(tmp_path / "recs.npy")
+    mp.spawn(_pdw_worker, args=(world, _free_port(), y, bounds, out_path), nprocs=world, join=True)
+    got = np.load(out_path)
+    ref, nf = orc.pdws(y.astype(np.complex128), D=8, fc_hz=1e9, fs_sps=8e6, t0=3.0)
+    assert np.allclose(got[-1][:8], nf, rtol=1e-6)
+    got = got[:-1]
+    assert len(ref) == len(got) == 7
+    for g, r in zip(got, ref):
+        assert (int(g[0]), int(g[1]), int(g[2]), int(g[8])) == (r.toa_row, r.end_row, r.channel, r.saturated)
+        assert abs(g[3] - r.amp) <= 1e-6 * r.amp and abs(g[5] - r.snr_db) <= 1e-5
+        assert abs(g[4] - r.freq_hz) <= 1e-3 * 1e6 / 360 and g[6] == r.toa_s and g[7] == r.pw_s
+
+
+def test_fold_exit_codes():
+    from sdr_channelizer_b200.sharding import fold_exit_codes
+    codes = [np.array([0, 1, 2, 3, 1, 0], dtype=np.uint8), np.array([2, 2, 2, 2, 3, 3], dtype=np.uint8)]
+    assert fold_exit_codes([], 6).tolist() == [0] * 6
+    assert fold_exit_codes(codes[:1], 6).tolist() == [0, 1, 0, 1, 1, 0]
+    assert fold_exit_codes(codes, 6).tolist() == [0, 1, 0, 1, 0, 1]

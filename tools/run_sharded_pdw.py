@@ -12,7 +12,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 import sdr_channelizer_b200 as pkg  # noqa: E402
-from sdr_channelizer_b200.sharding import gather_rows_to_rank  # noqa: E402
+from sdr_channelizer_b200.sharding import PdwShard, TorchDistComm, create_pdws_sharded, gather_rows_to_rank  # noqa: E402
 from tests import synth  # noqa: E402
 
 M, P, OS = 64, 16, 1
@@ -39,6 +39,15 @@ if rank == 0:
     recs, nf = ch.pdws_ptr(full.data_ptr(), full.shape[0], fs, 2.4e9, 0.0)
 torch.cuda.synchronize(); dist.barrier()
 dt = time.perf_counter() - t0
+# the same without moving y: distributed median (histogram all-reduce over NCCL) + boundary stitching
+comm = TorchDistComm()
+shard = PdwShard(ch, y_own.data_ptr(), y_own.shape[0], sh.row_begin, n // (M // OS), fs, 2.4e9, 0.0)
+drecs, dnf = create_pdws_sharded(shard, comm)                 # warm-up (NCCL communicator set-up)
+torch.cuda.synchronize(); dist.barrier()
+t1 = time.perf_counter()
+drecs, dnf = create_pdws_sharded(shard, comm)
+torch.cuda.synchronize(); dist.barrier()
+dt_dist = time.perf_counter() - t1
 if rank == 0:
     ch.reset()
     xs = torch.from_numpy(iq).to(dev)
@@ -48,7 +57,11 @@ if rank == 0:
     same_y = bool(torch.equal(full.view(torch.float32), ys.view(torch.float32)))
     same_pdw = len(ref) == len(recs) and all((a.channel, a.toa_row, a.end_row, a.amp, a.freq_hz, a.saturated) ==
                                              (b.channel, b.toa_row, b.end_row, b.amp, b.freq_hz, b.saturated) for a, b in zip(recs, ref))
+    same_dist = len(ref) == len(drecs) and all(bytes(a) == bytes(b) for a, b in zip(drecs, ref)) and bool(np.array_equal(dnf, nf1))
+    straddlers = sum(1 for r in ref if any(s_.row_begin < r.end_row and r.toa_row <= s_.row_begin for s_ in shards[1:]))
     print(json.dumps({"n_gpus": world, "samples": n, "rows": int(full.shape[0]), "pdws": len(recs), "seconds": dt,
-                      "stitched_rows_bit_identical_to_one_gpu": same_y, "pdws_identical_to_one_gpu": bool(same_pdw)}), flush=True)
+                      "stitched_rows_bit_identical_to_one_gpu": same_y, "pdws_identical_to_one_gpu": bool(same_pdw),
+                      "distributed_pdws_byte_identical_to_one_gpu": bool(same_dist), "distributed_pdw_seconds": dt_dist,
+                      "pulses_straddling_a_shard_boundary": straddlers}), flush=True)
 dist.barrier(); dist.destroy_process_group()
 ch.close()
