@@ -22,6 +22,13 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 n = M * 200_000
 iq, bw, fs = synth.pulsed_int16(n, M=M, seed=4242)          # every rank builds the same recording
+# bursts centred on the quarter points, so pulses straddle the shard boundaries of 2- and 4-GPU runs
+for q, f in ((0.25, 0.11), (0.5, -0.23), (0.75, 0.37)):
+    a, b = int(q * n) - 15000, int(q * n) + 22000
+    t = np.arange(b - a)
+    burst = 9000.0 * np.exp(2j * np.pi * f * t)
+    iq[a:b, 0] = np.clip(iq[a:b, 0] + np.round(burst.real), -32768, 32767).astype(iq.dtype)
+    iq[a:b, 1] = np.clip(iq[a:b, 1] + np.round(burst.imag), -32768, 32767).astype(iq.dtype)
 taps = pkg.design_prototype(M, P)
 shards = pkg.plan_time_shards(n, M, M * P, OS, world)
 sh = shards[rank]
