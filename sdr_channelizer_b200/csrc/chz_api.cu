@@ -70,7 +70,7 @@ static int launch_fused(::chz* h, ChanParams prm, cudaStream_t st) {
 
 template <int P, bool IN16, int MT>
 static int launch_fir_m(::chz* h, ChanParams prm, float2* u, cudaStream_t st) {
-  const int bpb = prm.M < 128 ? prm.M : 128, nbb = prm.M / bpb, groups = 128 / bpb;
+  const int bpb = prm.M < 128 ? prm.M : (prm.M % 128 == 0 ? 128 : 112), nbb = prm.M / bpb, groups = 128 / bpb;   // as in k_fir
   // 128 threads x <= 128 registers: 4 blocks resident per SM; span blocks per branch block = SMs*4 / nbb
   LaunchPlan lp = plan_spans(h, prm.nrows, P, groups, 4, (h->sm_count * 4 / nbb) > 0 ? (h->sm_count * 4 / nbb) : 1);
   prm.span_rows = lp.span_rows;
@@ -159,6 +159,8 @@ static int launch_fft_rows(::chz* h, const float2* u, float2* y, long long nrows
     case 16: return launch_fft_rows_t<16, 128, 256>(h, u, y, nrows, st);
     case 32: return launch_fft_rows_t<32, 64, 256>(h, u, y, nrows, st);
     case 64: return launch_fft_rows_t<64, 32, 256>(h, u, y, nrows, st);
+    case 56: return launch_fft_rows_t<56, 32, 256>(h, u, y, nrows, st);
+    case 560: return launch_fft_rows_t<560, 4, 256>(h, u, y, nrows, st);
     case 128: return launch_fft_rows_t<128, 16, 256>(h, u, y, nrows, st);
     case 256: return launch_fft_rows_t<256, 16, 256>(h, u, y, nrows, st);
     case 512: return launch_fft_rows_big<512, 8>(h, u, y, nrows, st);
@@ -210,6 +212,8 @@ static int launch_fused_dispatch(::chz* h, const ChanParams& prm, cudaStream_t s
     case 128: CHZ_FUSED_P(128, IN16)
     case 256: CHZ_FUSED_P(256, IN16)
     case 512: CHZ_FUSED_P(512, IN16)
+    case 56: CHZ_FUSED_P(56, IN16)
+    case 560: CHZ_FUSED_P(560, IN16)
     default: return 1;
   }
 }
@@ -413,7 +417,7 @@ static bool pipe_available(const ::chz* h) {
 }
 
 static bool fused_available(const ::chz* h) {
-  return !h->generic && h->M >= 8 && h->M <= 512 && (h->P == 8 || h->P == 12 || h->P == 16);
+  return !h->generic && h->M >= 8 && h->M <= 560 && (h->P == 8 || h->P == 12 || h->P == 16);
 }
 
 static int ensure_taps(::chz* h, uint32_t bw) {
@@ -620,7 +624,9 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
   h->device = dev;
   h->sm_count = prop.multiProcessorCount;
   h->M = M; h->os = oversample; h->D = M / oversample;
-  h->generic = M < 8 || (M & (M - 1)) != 0;   // no radix plan: direct FIR + O(M^2) row DFT kernels
+  // no radix plan: direct FIR + O(M^2) row DFT kernels.  56 = 8*7 and 560 = 16*5*7, the reference's own
+  // channel counts (create_pdws_channelized.m:31, generate_channelized_training_iq.m:95-96), have plans.
+  h->generic = (M < 8 || (M & (M - 1)) != 0) && M != 56 && M != 560;
   if (taps) {
     h->taps.assign(taps, taps + ntaps);
   } else {
@@ -656,6 +662,7 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
       case 128: r[0] = 16; r[1] = 8; break; case 256: r[0] = 16; r[1] = 16; break;
       case 512: r[0] = 16; r[1] = 8; r[2] = 4; break;   case 1024: r[0] = 16; r[1] = 8; r[2] = 8; break;
       case 2048: r[0] = 16; r[1] = 16; r[2] = 8; break; case 4096: r[0] = 16; r[1] = 16; r[2] = 16; break;
+      case 56: r[0] = 8; r[1] = 7; break;               case 560: r[0] = 16; r[1] = 5; r[2] = 7; break;
     }
     size_t off = 0;
     int ns = r[0];

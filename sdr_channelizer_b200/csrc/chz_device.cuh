@@ -87,7 +87,51 @@ __device__ __forceinline__ void dft16(float2* v) {
   #pragma unroll
   for (int i = 0; i < 16; i++) v[i] = t[i];
 }
+// Odd prime radices for the reference's natural channel counts (M = fs*1e-6 = 56 = 8*7,
+// matlab/create_pdws_channelized.m:31; 560 = 16*5*7, generate_channelized_training_iq.m:95-96):
+//   X_k = v_0 + sum_{m=1..(R-1)/2} [ (v_m + v_{R-m}) cos(2 pi k m / R) + j (v_m - v_{R-m}) sin(2 pi k m / R) ]
+// and X_{R-k} is the same with the second term negated.  Indices are compile-time after unrolling, so
+// the cosines/sines fold into immediates.
+__host__ __device__ constexpr float cos_r(int R, int i) {   // cos(2 pi i / R), R in {5, 7}, 0 <= i < R
+  return R == 5 ? (i == 0 ? 1.0f : (i == 1 || i == 4) ? 0.30901699437494742410f : -0.80901699437494742410f)
+                : (i == 0 ? 1.0f : (i == 1 || i == 6) ? 0.62348980185873353053f
+                   : (i == 2 || i == 5) ? -0.22252093395631440429f : -0.90096886790241912624f);
+}
+__host__ __device__ constexpr float sin_r(int R, int i) {   // sin(2 pi i / R)
+  return R == 5 ? (i == 0 ? 0.0f : i == 1 ? 0.95105651629515357212f : i == 2 ? 0.58778525229247312917f
+                   : i == 3 ? -0.58778525229247312917f : -0.95105651629515357212f)
+                : (i == 0 ? 0.0f : i == 1 ? 0.78183148246802980871f : i == 2 ? 0.97492791218182360702f
+                   : i == 3 ? 0.43388373911755812048f : i == 4 ? -0.43388373911755812048f
+                   : i == 5 ? -0.97492791218182360702f : -0.78183148246802980871f);
+}
+template <int R> __device__ __forceinline__ void dft_odd(float2* v) {
+  constexpr int H = (R - 1) / 2;
+  float2 a[H], b[H];
+  #pragma unroll
+  for (int m = 1; m <= H; m++) { a[m - 1] = cadd(v[m], v[R - m]); b[m - 1] = mul_j(csub(v[m], v[R - m])); }
+  float2 x0 = v[0];
+  #pragma unroll
+  for (int m = 0; m < H; m++) x0 = cadd(x0, a[m]);
+  float2 out[R];
+  out[0] = x0;
+  #pragma unroll
+  for (int k = 1; k <= H; k++) {
+    float2 re = v[0], im = make_float2(0.f, 0.f);
+    #pragma unroll
+    for (int m = 1; m <= H; m++) {
+      const float c = cos_r(R, (k * m) % R), sn = sin_r(R, (k * m) % R);
+      re = __ffma2_rn(make_float2(c, c), a[m - 1], re);
+      im = __ffma2_rn(make_float2(sn, sn), b[m - 1], im);
+    }
+    out[k] = cadd(re, im);
+    out[R - k] = csub(re, im);
+  }
+  #pragma unroll
+  for (int i = 0; i < R; i++) v[i] = out[i];
+}
 template <int R> __device__ __forceinline__ void dft(float2* v);
+template <> __device__ __forceinline__ void dft<5>(float2* v) { dft_odd<5>(v); }
+template <> __device__ __forceinline__ void dft<7>(float2* v) { dft_odd<7>(v); }
 template <> __device__ __forceinline__ void dft<2>(float2* v) { dft2(v[0], v[1]); }
 template <> __device__ __forceinline__ void dft<4>(float2* v) { dft4(v[0], v[1], v[2], v[3]); }
 template <> __device__ __forceinline__ void dft<8>(float2* v) { dft8(v); }
@@ -106,6 +150,13 @@ template <> struct Plan<512>  { static constexpr int np = 3; static constexpr in
 template <> struct Plan<1024> { static constexpr int np = 3; static constexpr int r0 = 16, r1 = 8,  r2 = 8; };
 template <> struct Plan<2048> { static constexpr int np = 3; static constexpr int r0 = 16, r1 = 16, r2 = 8; };
 template <> struct Plan<4096> { static constexpr int np = 3; static constexpr int r0 = 16, r1 = 16, r2 = 16; };
+template <> struct Plan<56>   { static constexpr int np = 2; static constexpr int r0 = 8,  r1 = 7,  r2 = 1; };   // fs = 56 MS/s, 1 MHz bins
+template <> struct Plan<560>  { static constexpr int np = 3; static constexpr int r0 = 16, r1 = 5,  r2 = 7; };   // 0.1 MHz bins
+
+// Threads of one group in the fused kernel: a branch per thread, rounded up to whole warps for M >= 32
+// (named barriers count whole warps); the spare lanes of a non-power-of-two M idle through the FIR and
+// work in the FFT passes.
+template <int M> struct GroupThreads { static constexpr int value = M < 32 ? M : (M + 31) / 32 * 32; };
 
 // Padded element index inside one row of the shared tile (8-byte elements, 16 per 128-byte bank
 // row).  One pad element per 2^PadShift elements, and a row stride chosen so that the half-warps of
@@ -114,10 +165,10 @@ template <> struct Plan<4096> { static constexpr int np = 3; static constexpr in
 //   M = 32 (radix 8,4):  4 butterflies per row  -> pad every 8, rows 4 bank pairs apart (stride 36)
 //   M = 64 (radix 8,8):  8 butterflies per row  -> pad every 8, rows 8 apart           (stride 72)
 //   M >= 128 (first radix 16): pad every 16, rows 8 apart for M = 128, irrelevant above
-template <int M> struct PadShift { static constexpr int value = (M == 32 || M == 64) ? 3 : 4; };
+template <int M> struct PadShift { static constexpr int value = (M == 32 || M == 64 || M == 56) ? 3 : 4; };
 template <int M> __device__ __forceinline__ int padi(int i) { return i + (i >> PadShift<M>::value); }
 template <int M> struct RowStride {
-  static constexpr int value = M == 32 ? 36 : (M == 64 ? 72 : M + M / 16 + (M < 16 ? 1 : 0));
+  static constexpr int value = M == 32 ? 36 : (M == 64 ? 72 : (M == 56 ? 72 : M + M / 16 + (M < 16 ? 1 : 0)));
 };
 
 // One Stockham pass of radix R over ROWS rows of length M held in shared memory, NT threads.
@@ -145,7 +196,7 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, fl
     float2 v[R];
     #pragma unroll
     for (int q = 0; q < R; q++) v[q] = s[padi<M>(j + q * BPR)];
-    const int k = j & (NS - 1);         // j mod NS
+    const int k = j % NS;               // NS is a compile-time constant (a power of two except in Plan<560>)
     if (NS > 1) {
       // twiddle table layout (host: build_twiddles): per pass, entry (q-1)*NS + k holds
       // W_{NS R}^{q k}; the lanes of a warp read consecutive k -> consecutive addresses, no conflicts

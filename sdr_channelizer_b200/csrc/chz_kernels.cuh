@@ -183,10 +183,11 @@ __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, 
 template <int P, bool IN16, int MT>
 __global__ void __launch_bounds__(128, 4) k_fir(ChanParams prm, float2* __restrict__ u) {
   const int Mv = MT ? MT : prm.M;
-  const int bpb = Mv < 128 ? Mv : 128;             // branches per block
+  const int bpb = Mv < 128 ? Mv : (Mv % 128 == 0 ? 128 : 112);   // branches per block (560 = 5 x 112)
   const int nbb = Mv / bpb;                        // branch blocks
   const int groups = 128 / bpb;                    // spans handled side by side in one block
   const int bb = blockIdx.x % nbb, g = threadIdx.x / bpb;
+  if (g >= groups) return;                         // 128 is not a multiple of bpb (M = 56: 16 spare threads)
   const int p = bb * bpb + threadIdx.x % bpb;
   const long long nspans = prm.spans_per_phase * prm.os;
   const long long sstride = (long long)(gridDim.x / nbb) * groups;
@@ -328,8 +329,9 @@ __global__ void __launch_bounds__(256, 2) k_fft_rows_big(const float2* u, float2
 // A block is G groups of M threads; a group walks spans of rows.  Every RT filtered rows (RT divides
 // P) the group runs the M-point FFT on its shared tile and streams the result to global memory.
 template <int M, int P> struct FusedCfg {
-  static constexpr int NT = M < 256 ? 256 : M;       // threads per block
-  static constexpr int G = NT / M;                   // groups per block
+  static constexpr int MG = GroupThreads<M>::value;  // threads per group (M rounded up to whole warps)
+  static constexpr int NT = MG < 256 ? 256 / MG * MG : MG;   // threads per block
+  static constexpr int G = NT / MG;                  // groups per block
   // rows per FFT tile: largest divisor of P keeping the two tile buffers of a block under ~72 KB
   static constexpr int RTMAX = (72 * 1024) / (2 * 8 * RowStride<M>::value * G);
   static constexpr int RT = RTMAX >= P ? P : (P % 8 == 0 && RTMAX >= 8 ? 8 : (P % 6 == 0 && RTMAX >= 6 ? 6 : (P % 4 == 0 && RTMAX >= 4 ? 4 : (P % 2 == 0 && RTMAX >= 2 ? 2 : 1))));
@@ -337,7 +339,7 @@ template <int M, int P> struct FusedCfg {
 };
 
 template <int M> __device__ __forceinline__ void group_sync(int g) {
-  if (M >= 64) asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(M) : "memory");   // named barrier per group
+  if (M > 32) asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GroupThreads<M>::value) : "memory");   // named barrier per group
   else __syncwarp();   // M <= 32: a group lives inside one warp
 }
 
@@ -345,15 +347,19 @@ template <int M, int P, bool IN16>
 __global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 ? CHZ_FUSED_MINB : 1) k_chan_fused(ChanParams prm) {
   extern __shared__ float2 smem[];
   typedef FusedCfg<M, P> CF;
-  constexpr int NT = CF::NT, G = CF::G, RT = CF::RT, S = RowStride<M>::value;
-  constexpr bool TWREG = TwReg<M, M>::value;
+  constexpr int NT = CF::NT, G = CF::G, RT = CF::RT, S = RowStride<M>::value, MG = CF::MG;
+  constexpr bool TWREG = TwReg<M, MG>::value;
   float2* tw = smem;                                  // M twiddles
-  const int g = threadIdx.x / M, p = threadIdx.x % M;
+  const int g = threadIdx.x / MG, t = threadIdx.x % MG;
+  // non-power-of-two M: the spare lanes of the last warp shadow branch M-1 through the FIR (same control
+  // flow, so they meet every barrier) without storing, and take their share of the FFT butterflies
+  const bool branch = MG == M || t < M;
+  const int p = branch ? t : M - 1;
   float2* buf0 = smem + M + (size_t)g * 2 * RT * S;   // [RT][S]
   float2* buf1 = buf0 + RT * S;
   for (int i = threadIdx.x; i < M; i += NT) tw[i] = prm.tw[i];
-  float2 twr[TwReg<M, M>::count];
-  load_last_pass_twiddles<M, M>(prm.tw, p, twr);
+  float2 twr[TwReg<M, MG>::count];
+  load_last_pass_twiddles<M, MG>(prm.tw, t, twr);
   __syncthreads();
   const long long nspans = prm.spans_per_phase * prm.os;
   const long long rstride = (long long)prm.os * M;
@@ -363,15 +369,15 @@ __global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 
     const int r = padi<M>((p - sp.shift + M) % M);
     float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
     fir_span<P, IN16, M, 0>(prm, sp, p, [&](int ii, long long i, float2 v) {
-      buf0[(ii % RT) * S + r] = v;
+      if (branch) buf0[(ii % RT) * S + r] = v;
       if (ii % RT == RT - 1) {
         group_sync<M>(g);
         const long long i0 = i - (RT - 1);
         const long long left = sp.count - i0;
         const int vhi = (int)(left < RT ? (left < 0 ? 0 : left) : RT);       // rows [vlo, vhi) of the tile are stored
         const int vlo = i0 < sp.skip ? (int)(sp.skip - i0) : 0;
-        fft_tile_to_global<M, RT, M, TWREG>(buf0, buf1, tw, twr, p, gout + i0 * rstride, rstride, vlo, vhi,
-                                            [&] { group_sync<M>(g); });
+        fft_tile_to_global<M, RT, MG, TWREG>(buf0, buf1, tw, twr, t, gout + i0 * rstride, rstride, vlo, vhi,
+                                             [&] { group_sync<M>(g); });
         if (Plan<M>::np != 2) group_sync<M>(g);   // the last pass of 1- and 3-pass plans reads buf0
       }
     });

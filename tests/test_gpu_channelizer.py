@@ -47,7 +47,7 @@ def test_unpack_bit_exact_all_values(orc, bw):
 
 
 # ---- K3 against cuFFT ----------------------------------------------------------------------------------
-@pytest.mark.parametrize("M", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("M", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 56, 560])   # 56 = 8*7, 560 = 16*5*7: radix-7/5 passes
 def test_fft_stage_matches_cufft(M):
     torch = _torch()
     rows = 37 if M >= 1024 else 333
@@ -107,7 +107,8 @@ def test_channelizer_matches_oracle(orc, M, P, os_, kind, n):
                                           (64, 16, 1, 2), (1024, 16, 2, 0), (4096, 8, 1, 0), (64, 24, 1, 0), (64, 32, 2, 0),
                                           (4096, 16, 1, 3), (2048, 16, 2, 3), (1024, 8, 1, 3), (64, 16, 1, 4), (64, 16, 2, 4), (64, 12, 1, 4), (64, 8, 2, 4),
                                           (1024, 16, 1, 5), (1024, 16, 2, 5), (1024, 12, 2, 5), (1024, 8, 1, 5),
-                                          (4096, 16, 1, 6), (2048, 16, 2, 6), (1024, 8, 1, 6), (1024, 12, 2, 6), (1024, 16, 2, 6), (2048, 12, 1, 6)])
+                                          (4096, 16, 1, 6), (2048, 16, 2, 6), (1024, 8, 1, 6), (1024, 12, 2, 6), (1024, 16, 2, 6), (2048, 12, 1, 6),
+                                          (56, 12, 1, 1), (56, 16, 2, 1), (56, 8, 1, 1), (56, 12, 2, 2), (560, 12, 1, 1), (560, 16, 2, 1), (560, 8, 1, 1), (560, 12, 2, 2)])
 def test_random_taps_every_tap_index_matters(orc, M, P, os_, path):
     """A designed prototype has tiny end taps, which would hide a mis-indexed tap or window slot
     below the 1e-5 tolerance; with random taps of equal weight any such slip is an O(1/P) error."""
@@ -126,7 +127,7 @@ def test_random_taps_every_tap_index_matters(orc, M, P, os_, path):
     ch.close()
 
 
-@pytest.mark.parametrize("M,P,os_", [(64, 16, 1), (64, 16, 2), (256, 12, 1), (8, 8, 1)])
+@pytest.mark.parametrize("M,P,os_", [(64, 16, 1), (64, 16, 2), (256, 12, 1), (8, 8, 1), (56, 12, 1), (56, 12, 2), (560, 12, 1)])
 def test_split_path_equals_fused_path(M, P, os_):
     _torch()
     iq, bw = synth.tones_int16_q11(M * 900 + 5, M, seed=3)
@@ -273,7 +274,8 @@ def test_edge_lengths_ragged_and_tiny(orc, M, P, os_, bw):
                                          (100, 16, 2, "full"), (560, 12, 1, "q11"), (4, 8, 1, "i8"), (2, 3, 2, "full")])
 def test_non_power_of_two_channel_counts(orc, M, P, os_, kind):
     """The reference's own M is fs*1e-6 (56 for the b200mini at 56 MS/s, create_pdws_channelized.m:31);
-    such sizes run the functional any-M path.  Same tolerance, and streaming stays bit-identical."""
+    56 and 560 have radix-7/5 plans and run the fused kernel, every other such size runs the functional
+    any-M path.  Same tolerance, and streaming stays bit-identical."""
     _torch()
     n = M * 300 + 5
     iq, bw = _gen(kind, n, M, seed=M)
