@@ -282,33 +282,35 @@ static int launch_ws_dispatch(::chz* h, const ChanParams& prm, cudaStream_t st) 
 static bool ws_available(const ::chz* h) { return h->M == 64 && (h->P == 8 || h->P == 12 || h->P == 16); }
 
 // Cluster path (M = 1024, 2048, 4096): returns 1 when there is no instantiation for (M, P).
-template <int M, int P, bool IN16>
+template <int M, int P, bool IN16, int TPC, bool PIPE>
 static int launch_cluster(::chz* h, ChanParams prm, cudaStream_t st) {
-  typedef ClusterCfg<M, P> CC;
+  typedef ClusterCfg<M, P, TPC> CC;
   if constexpr (!CC::ok) {
     return 1;
   } else {
-    auto kern = k_chan_cluster<M, P, IN16>;
+    auto kern = k_chan_cluster<M, P, IN16, TPC, PIPE>;
+    constexpr int NSLOT = PIPE ? 4 : 2;
     static thread_local int nclusters_dev[kMaxDev] = {0};
     int& nclusters = nclusters_dev[h->device % kMaxDev];
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
+    cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CC::C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = CC::SMEM; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(TPC); cfg.dynamicSmemBytes = CC::SMEM; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
     if (!nclusters) {
       CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CC::SMEM));
-      cfg.gridDim = dim3((unsigned)(h->sm_count / CC::C * CC::C));
+      if (CC::C > 8) CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      cfg.gridDim = dim3((unsigned)(h->sm_count * (TPC == 512 ? 1 : 2) / CC::C * CC::C));
       int n = 0;
       CHZ_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
       nclusters = n > 0 ? n : 1;
+      if (std::getenv("CHZ_TRACE_LAUNCH")) std::fprintf(stderr, "[chz] cluster kernel M=%d TPC=%d: %d clusters of %d CTAs resident\n", M, TPC, nclusters, CC::C);
     }
     const LaunchPlan lp = plan_spans(h, prm.nrows, P, 1, 1, nclusters);
     prm.span_rows = lp.span_rows;
     prm.spans_per_phase = lp.spans_per_phase;
     const unsigned ncl = lp.grid.x;   // <= nclusters
-    CHZ_CUDA(h->cluster_ring.reserve((size_t)nclusters * 2 * P * M * sizeof(float2)));
+    CHZ_CUDA(h->cluster_ring.reserve((size_t)nclusters * NSLOT * P * M * sizeof(float2)));
     cfg.gridDim = dim3(ncl * CC::C);
     float2* ring = (float2*)h->cluster_ring.p;
     CHZ_CUDA(cudaLaunchKernelEx(&cfg, kern, prm, ring));
@@ -317,13 +319,13 @@ static int launch_cluster(::chz* h, ChanParams prm, cudaStream_t st) {
   }
 }
 
-template <bool IN16>
+template <bool IN16, int TPC, bool PIPE>
 static int launch_cluster_dispatch(::chz* h, const ChanParams& prm, cudaStream_t st) {
-#define CHZ_CL_P(MV)                                                   \
-  switch (h->P) {                                                      \
-    case 8: return launch_cluster<MV, 8, IN16>(h, prm, st);            \
-    case 16: return launch_cluster<MV, 16, IN16>(h, prm, st);          \
-    default: return 1;                                                 \
+#define CHZ_CL_P(MV)                                                        \
+  switch (h->P) {                                                           \
+    case 8: return launch_cluster<MV, 8, IN16, TPC, PIPE>(h, prm, st);      \
+    case 16: return launch_cluster<MV, 16, IN16, TPC, PIPE>(h, prm, st);    \
+    default: return 1;                                                      \
   }
   switch (h->M) {
     case 1024: CHZ_CL_P(1024)
@@ -334,11 +336,57 @@ static int launch_cluster_dispatch(::chz* h, const ChanParams& prm, cudaStream_t
 #undef CHZ_CL_P
 }
 
-static bool cluster_available(const ::chz* h) {
+static bool cluster_available(const ::chz* h, int tpc) {
   if (h->M != 1024 && h->M != 2048 && h->M != 4096) return false;
-  const uint32_t C = h->M / 512;
+  const uint32_t C = h->M / tpc;
+  if (tpc == 256) return h->P == 16 && C <= 16;
   return (h->P == 8 || h->P == 16) && h->P % C == 0;
 }
+
+// DSMEM cluster kernel (st.async + mbarrier hand-off): returns 1 when there is no instantiation for (M, P).
+template <int M, int P, bool IN16>
+static int launch_dsm(::chz* h, ChanParams prm, cudaStream_t st) {
+  typedef DsmCfg<M, P> DC;
+  if constexpr (!DC::ok) {
+    return 1;
+  } else {
+    auto kern = k_chan_dsm<M, P, IN16>;
+    static thread_local int nclusters_dev[kMaxDev] = {0};
+    int& nclusters = nclusters_dev[h->device % kMaxDev];
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = DC::C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(DC::TPC); cfg.dynamicSmemBytes = DC::SMEM; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    if (!nclusters) {
+      CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DC::SMEM));
+      if (DC::C > 8) CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      cfg.gridDim = dim3((unsigned)(h->sm_count * 2 / DC::C * DC::C));
+      int n = 0;
+      CHZ_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      nclusters = n > 0 ? n : 1;
+      if (std::getenv("CHZ_TRACE_LAUNCH")) std::fprintf(stderr, "[chz] dsm kernel M=%d: %d clusters of %d CTAs resident\n", M, nclusters, DC::C);
+    }
+    const LaunchPlan lp = plan_spans(h, prm.nrows, P, 1, 1, nclusters);
+    prm.span_rows = lp.span_rows;
+    prm.spans_per_phase = lp.spans_per_phase;
+    cfg.gridDim = dim3(lp.grid.x * DC::C);   // lp.grid.x <= nclusters
+    CHZ_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
+    h->launches++;
+    return CHZ_OK;
+  }
+}
+template <bool IN16>
+static int launch_dsm_dispatch(::chz* h, const ChanParams& prm, cudaStream_t st) {
+  if (h->P != 16) return 1;
+  switch (h->M) {
+    case 1024: return launch_dsm<1024, 16, IN16>(h, prm, st);
+    case 2048: return launch_dsm<2048, 16, IN16>(h, prm, st);
+    case 4096: return launch_dsm<4096, 16, IN16>(h, prm, st);
+    default: return 1;
+  }
+}
+static bool dsm_available(const ::chz* h) { return (h->M == 1024 || h->M == 2048 || h->M == 4096) && h->P == 16; }
 
 // Pipelined split path (M = 1024, 2048, 4096): one persistent launch, FIR and in-place FFT tasks from one
 // ordered ticket queue (k_chan_pipe).  Returns 1 when there is no instantiation for (M, P).
@@ -450,16 +498,23 @@ static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, 
     // The cluster kernel is opt-in (CHZ_OPT_FORCE_PATH = 3): measured on B200 it is slower than the
     // split path (cfg4: 27.8 % vs 39.3 % of the HBM roofline; only 120 of 148 SMs host 8-CTA clusters and
     // each tile serialises FIR -> release fence -> cluster barrier -> L2 reads -> 3 FFT passes).
-    const bool cluster = cluster_available(h) && h->force_path == 3;
-    if (h->force_path == 3 && !cluster) return CHZ_EINVAL;
+    const bool cl_path = h->force_path == 3 || h->force_path == 7 || h->force_path == 8 || h->force_path == 9;
+    const int cl_tpc = (h->force_path == 7 || h->force_path == 8) ? 256 : 512;
+    const bool cluster = cl_path && cluster_available(h, cl_tpc);
+    if (cl_path && !cluster) return CHZ_EINVAL;
     const bool ws = ws_available(h) && h->force_path == 4;
     if (h->force_path == 4 && !ws) return CHZ_EINVAL;
     if (h->force_path == 1 && !fused) return CHZ_EINVAL;
     const bool dit2 = dit2_available(h) && h->force_path == 5;
     if (h->force_path == 5 && !dit2) return CHZ_EINVAL;
+    const bool dsm = dsm_available(h) && h->force_path == 10;
+    if (h->force_path == 10 && !dsm) return CHZ_EINVAL;
     const bool pipe = pipe_available(h) && h->force_path == 6;
     if (h->force_path == 6 && !pipe) return CHZ_EINVAL;
-    if (pipe) {
+    if (dsm) {
+      rc = in16 ? launch_dsm_dispatch<true>(h, prm, st) : launch_dsm_dispatch<false>(h, prm, st);
+      if (rc) return rc == 1 ? CHZ_EINVAL : rc;
+    } else if (pipe) {
       rc = in16 ? launch_pipe_dispatch<true>(h, prm, st) : launch_pipe_dispatch<false>(h, prm, st);
       if (rc) return rc == 1 ? CHZ_EINVAL : rc;
     } else if (dit2) {
@@ -469,7 +524,12 @@ static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, 
       rc = in16 ? launch_ws_dispatch<true>(h, prm, st) : launch_ws_dispatch<false>(h, prm, st);
       if (rc) return rc == 1 ? CHZ_EINVAL : rc;
     } else     if (cluster) {
-      rc = in16 ? launch_cluster_dispatch<true>(h, prm, st) : launch_cluster_dispatch<false>(h, prm, st);
+      switch (h->force_path) {
+        case 7: rc = in16 ? launch_cluster_dispatch<true, 256, false>(h, prm, st) : launch_cluster_dispatch<false, 256, false>(h, prm, st); break;
+        case 8: rc = in16 ? launch_cluster_dispatch<true, 256, true>(h, prm, st) : launch_cluster_dispatch<false, 256, true>(h, prm, st); break;
+        case 9: rc = in16 ? launch_cluster_dispatch<true, 512, true>(h, prm, st) : launch_cluster_dispatch<false, 512, true>(h, prm, st); break;
+        default: rc = in16 ? launch_cluster_dispatch<true, 512, false>(h, prm, st) : launch_cluster_dispatch<false, 512, false>(h, prm, st); break;
+      }
       if (rc == 1) return CHZ_EINVAL;
       if (rc) return rc;
     } else if (fused) {
@@ -745,7 +805,7 @@ int chz_set_option(chz_t* h, int opt, int64_t value) {
   switch (opt) {
     case CHZ_OPT_RETAIN: h->retain = value != 0; return CHZ_OK;
     case CHZ_OPT_CHUNK_ROWS: if (value < 0) return CHZ_EINVAL; h->chunk_rows = value; return CHZ_OK;
-    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 6) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
+    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 10) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
     default: return CHZ_EINVAL;
   }
 }

@@ -491,10 +491,11 @@ __global__ void __launch_bounds__(256, 3) k_chan_ws(ChanParams prm) {
 // to the output.  The ring is double buffered: tile t+2 reuses tile t's slot only after barrier t+1,
 // which every CTA reaches after finishing its FFT of tile t.
 // DRAM traffic is the fused kernel's (raw in once, fp32 out once); the intermediate costs L2 bandwidth.
-template <int M, int P> struct ClusterCfg {
-  static constexpr int C = M / 512;                  // CTAs per cluster
+template <int M, int P, int TPC = 512> struct ClusterCfg {
+  static constexpr int C = M / TPC;                  // CTAs per cluster
   static constexpr int RPC = P / C;                  // rows each CTA transforms per tile
-  static constexpr bool ok = (M == 1024 || M == 2048 || M == 4096) && (P % C == 0) && RPC >= 1;
+  static constexpr bool ok = (M == 1024 || M == 2048 || M == 4096) && C >= 2 && C <= 16 && (P % C == 0) && RPC >= 1 &&
+                             (TPC == 512 || RPC * (M / 16) == TPC);
   // two FFT tile buffers + the inter-pass twiddle table (the cluster barrier invalidates L1 every tile,
   // so twiddles read through L1 would come from L2 again each time)
   static constexpr size_t SMEM = ((size_t)2 * (RPC > 0 ? RPC : 1) * RowStride<M>::value + M) * sizeof(float2);
@@ -505,61 +506,225 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int M, int P, bool IN16>
-__global__ void __launch_bounds__(512, 1) k_chan_cluster(ChanParams prm, float2* __restrict__ scratch) {
-  typedef ClusterCfg<M, P> CC;
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// TPC = threads (= branches) per CTA.  512: one CTA per SM (all registers).  256 (CHZ_OPT_FORCE_PATH=7,8):
+// twice as many CTAs per cluster, two CTAs of DIFFERENT clusters share an SM, so one cluster's barrier /
+// L2 latency overlaps the other's FIR or FFT.
+// PIPE (CHZ_OPT_FORCE_PATH=8): software pipelining across the cluster barrier.  After the FIR of tile t a CTA
+// only ARRIVES (release) at the barrier, waits for the barrier of tile t-1 -- which everyone reached a whole
+// FIR tile ago -- and transforms tile t-1, so neither the barrier round trip nor the slowest CTA of the
+// cluster is on the critical path.  The ring then needs 4 slots: a CTA can be writing tile t+3 while a slow
+// one still reads tile t (it is only known to have arrived for t+1).
+template <int M, int P, bool IN16, int TPC, bool PIPE>
+__global__ void __launch_bounds__(TPC, TPC == 512 ? 1 : 2) k_chan_cluster(ChanParams prm, float2* __restrict__ scratch) {
+  typedef ClusterCfg<M, P, TPC> CC;
   typedef Plan<M> PL;
   static_assert(PL::np == 3 && PL::r0 == 16, "large-M plan expected");
-  constexpr int C = CC::C, RPC = CC::RPC, S = RowStride<M>::value, BPR0 = M / 16;
+  constexpr int C = CC::C, RPC = CC::RPC, S = RowStride<M>::value, BPR0 = M / 16, NSLOT = PIPE ? 4 : 2;
   extern __shared__ float2 smem[];
   float2* bufA = smem;
   float2* bufB = bufA + RPC * S;
   float2* tw = bufB + RPC * S;
   const int t = threadIdx.x;
-  for (int i = t; i < M; i += 512) tw[i] = prm.tw[i];
+  for (int i = t; i < M; i += TPC) tw[i] = prm.tw[i];
   __syncthreads();
   const int rank = (int)cluster_ctarank();
   const long long cid = blockIdx.x / C, ncl = gridDim.x / C;
-  const int p = rank * 512 + t;
-  float2* ring = scratch + (size_t)cid * 2 * P * M;
+  const int p = rank * TPC + t;
+  float2* ring = scratch + (size_t)cid * NSLOT * P * M;
   const long long nspans = prm.spans_per_phase * prm.os;
   const long long rstride = (long long)prm.os * M;
   const int frow = t / BPR0, fj = t % BPR0;            // this thread's first-pass butterfly: (row, column)
   unsigned tile = 0;
+  // transform rows [rank*RPC, rank*RPC + RPC) of the tile in `slot` and stream them to gout (+ row stride):
+  // passes 1 and 2 (ring -> shared memory), then pass 3 (shared memory -> global)
+  auto fft_tile_a = [&](const float2* slot) {
+    if (frow < RPC) {                                  // pass 1 (radix 16) from the ring, bypassing L1 (another SM wrote it)
+      float2 x[16];
+      const float2* src = slot + (size_t)(rank * RPC + frow) * M + fj;
+      #pragma unroll
+      for (int q = 0; q < 16; q++) x[q] = __ldcg(src + q * BPR0);
+      dft<16>(x);
+      float2* d = bufA + frow * S;
+      #pragma unroll
+      for (int q = 0; q < 16; q++) d[padi<M>(fj * 16 + q)] = x[q];
+    }
+    __syncthreads();
+    stockham_pass<M, PL::r1, PL::r0, RPC, TPC, false, false>(bufA, bufB, tw, nullptr, t, nullptr, 0, 0, 0);
+    __syncthreads();
+  };
+  auto fft_tile_b = [&](float2* gout0, int vlo, int vhi) {
+    stockham_pass<M, PL::r2, PL::r0 * PL::r1, RPC, TPC, true, false>(bufB, bufA, tw, nullptr, t, gout0, rstride, vlo, vhi);
+  };
+  // PIPE: the tile whose barrier has been arrived at but whose FFT is still to do
+  bool pend = false;
+  const float2* pend_slot = nullptr;
+  float2* pend_gout = nullptr;
+  int pend_vlo = 0, pend_vhi = 0;
   for (long long s = cid; s < nspans; s += ncl) {      // cluster-uniform loop
     const Span sp = make_span(prm, s);
     if (sp.count <= 0) continue;
     const int r = (p - sp.shift + M) % M;              // circular shift of the oversampled odd rows
     float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
     fir_span<P, IN16, M, 0>(prm, sp, p, [&](int ii, long long i, float2 v) {
-      float2* slot = ring + (size_t)(tile & 1) * P * M;
+      float2* slot = ring + (size_t)(tile % NSLOT) * P * M;
       slot[(size_t)ii * M + r] = v;
       if (ii == P - 1) {
-        cluster_barrier();                             // the whole tile is in the ring (L2)
         const long long i0 = i - (P - 1) + rank * RPC; // first span row this CTA transforms
         const long long left = sp.count - i0;
         const int vhi = (int)(left < RPC ? (left < 0 ? 0 : left) : RPC);
         const int vlo = i0 < sp.skip ? (int)(sp.skip - i0) : 0;
-        // pass 1 (radix 16) from the ring, bypassing L1 (another SM wrote it)
-        float2 x[16];
-        const float2* src = slot + (size_t)(rank * RPC + frow) * M + fj;
-        #pragma unroll
-        for (int q = 0; q < 16; q++) x[q] = __ldcg(src + q * BPR0);
-        dft<16>(x);
-        {
-          float2* d = bufA + frow * S;
-          #pragma unroll
-          for (int q = 0; q < 16; q++) d[padi<M>(fj * 16 + q)] = x[q];
+        if constexpr (PIPE) {
+          // The release fence of the arrive waits for every store this CTA has in flight.  Placed between
+          // passes 2 and 3 of the previous tile's FFT it finds this tile's ring stores (issued a thousand
+          // cycles ago) and the previous y rows (a whole tile ago) already acknowledged; right after the FIR
+          // it cost a third of all stall samples (profiles/r01k).
+          if (pend) { cluster_wait(); fft_tile_a(pend_slot); }   // tile-1 is complete in the ring
+          cluster_arrive();                            // my part of this tile is written
+          if (pend) fft_tile_b(pend_gout, pend_vlo, pend_vhi);
+          pend = true; pend_slot = slot; pend_gout = gout + i0 * rstride; pend_vlo = vlo; pend_vhi = vhi;
+        } else {
+          cluster_barrier();                           // the whole tile is in the ring (L2)
+          fft_tile_a(slot);
+          fft_tile_b(gout + i0 * rstride, vlo, vhi);
         }
-        __syncthreads();
-        stockham_pass<M, PL::r1, PL::r0, RPC, 512, false, false>(bufA, bufB, tw, nullptr, t, nullptr, 0, 0, 0);
-        __syncthreads();
-        stockham_pass<M, PL::r2, PL::r0 * PL::r1, RPC, 512, true, false>(bufB, bufA, tw, nullptr, t,
-                                                                         gout + i0 * rstride, rstride, vlo, vhi);
         tile++;
       }
     });
   }
+  if constexpr (PIPE) {
+    if (pend) { cluster_wait(); fft_tile_a(pend_slot); fft_tile_b(pend_gout, pend_vlo, pend_vhi); }
+  }
+}
+
+// ---- large M fused over distributed shared memory: st.async + mbarrier transaction counts -------------
+// Profile of the L2-ring cluster kernel (profiles/r01k): a third of all stall samples sit on the MEMBAR /
+// ERRBAR of `barrier.cluster.arrive.release` (every tile each CTA must drain its ring stores to L2 before
+// it may signal), the ring costs 16 B/sample of L2 bandwidth and half of it is written back to DRAM.
+// Here the FIR threads send every filtered value straight into the shared memory of the CTA that will
+// transform that row (`st.async.shared::cluster ... mbarrier::complete_tx::bytes`); the receiver waits on
+// a local mbarrier until RPC*M*8 bytes have landed.  No fence, no ring, no global intermediate.
+//   cluster = M/256 CTAs of 256 threads (= branches), two CTAs (of different clusters) per SM;
+//   tile t  = P rows; CTA `rank` transforms rows [rank*RPC, rank*RPC + RPC) of every tile (RPC = P/C);
+//   IN[2]   = receive buffers [RPC][RowStride] (padded layout, also the Stockham scratch of passes 2/3);
+//   flow control: a CTA may send tile t only after every CTA has finished the FFT of tile t-2 (same IN slot):
+//   one RELAXED cluster barrier per tile, arrive after the FFT of tile t-1, wait before the first send of t+1.
+// Software pipeline per CTA: FIR(t) [sends] -> FFT(t-1) [data arrived a whole FIR ago].
+template <int M, int P> struct DsmCfg {
+  static constexpr int TPC = 256;
+  static constexpr int C = M / TPC;
+  static constexpr int RPC = P / (C > 0 ? C : 1);
+  static constexpr bool ok = (M == 1024 || M == 2048 || M == 4096) && (P % C == 0) && RPC * (M / 16) == TPC;
+  static constexpr size_t SMEM = (size_t)3 * (RPC > 0 ? RPC : 1) * RowStride<M>::value * sizeof(float2);
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned local, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f2(unsigned remote_addr, float2 v, unsigned remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(remote_addr), "f"(v.x), "f"(v.y), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
+               ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_plain() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+
+template <int M, int P, bool IN16>
+__global__ void __launch_bounds__(256, 2) k_chan_dsm(ChanParams prm) {
+  typedef DsmCfg<M, P> DC;
+  typedef Plan<M> PL;
+  static_assert(PL::np == 3 && PL::r0 == 16, "large-M plan expected");
+  constexpr int TPC = DC::TPC, C = DC::C, RPC = DC::RPC, S = RowStride<M>::value, BPR0 = M / 16;
+  constexpr unsigned TILE_BYTES = (unsigned)(RPC * M * sizeof(float2));
+  extern __shared__ float2 smem[];
+  __shared__ __align__(8) uint64_t full[2];
+  float2* in0 = smem;                                  // IN[0] / Stockham scratch B of even tiles
+  float2* in1 = in0 + RPC * S;
+  float2* bufA = in1 + RPC * S;
+  const int t = threadIdx.x;
+  const unsigned rank = cluster_ctarank();
+  if (t == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&full[0], TILE_BYTES);               // tiles 0 and 1
+    mbar_expect_tx(&full[1], TILE_BYTES);
+  }
+  cluster_barrier();                                   // barriers initialised cluster-wide before anyone sends
+  const long long cid = blockIdx.x / C, ncl = gridDim.x / C;
+  const int p = (int)rank * TPC + t;
+  const long long nspans = prm.spans_per_phase * prm.os;
+  const long long rstride = (long long)prm.os * M;
+  const int frow = t / BPR0, fj = t % BPR0;            // first-pass butterfly of this thread: (row, column)
+  const unsigned in_addr[2] = {smem_u32(in0), smem_u32(in1)};
+  const unsigned full_addr[2] = {smem_u32(&full[0]), smem_u32(&full[1])};
+  unsigned tile = 0;                                   // tiles sent so far
+  // FFT of the tile in slot s (tile index n): wait for its bytes, three passes, stream rows to gout0
+  auto fft_tile = [&](unsigned n, float2* gout0, int vlo, int vhi) {
+    const unsigned sl = n & 1;
+    float2* in = sl ? in1 : in0;
+    mbar_wait(&full[sl], (n >> 1) & 1);
+    {
+      float2 x[16];
+      const float2* src = in + frow * S;
+      #pragma unroll
+      for (int q = 0; q < 16; q++) x[q] = src[padi<M>(fj + q * BPR0)];
+      dft<16>(x);
+      float2* d = bufA + frow * S;
+      #pragma unroll
+      for (int q = 0; q < 16; q++) d[padi<M>(fj * 16 + q)] = x[q];
+    }
+    __syncthreads();                                   // IN[sl] fully consumed: it becomes the pass-2 output
+    if (t == 0) mbar_expect_tx(&full[sl], TILE_BYTES);  // arm the slot for tile n+2 (senders are held by the cluster barrier)
+    stockham_pass<M, PL::r1, PL::r0, RPC, TPC, false, false>(bufA, in, prm.tw, nullptr, t, nullptr, 0, 0, 0);
+    __syncthreads();
+    stockham_pass<M, PL::r2, PL::r0 * PL::r1, RPC, TPC, true, false>(in, bufA, prm.tw, nullptr, t, gout0, rstride, vlo, vhi);
+  };
+  bool pend = false;
+  unsigned pend_n = 0;
+  float2* pend_gout = nullptr;
+  int pend_vlo = 0, pend_vhi = 0;
+  for (long long s = cid; s < nspans; s += ncl) {      // cluster-uniform loop
+    const Span sp = make_span(prm, s);
+    if (sp.count <= 0) continue;
+    const unsigned pos = (unsigned)padi<M>((p - sp.shift + M) % M) * (unsigned)sizeof(float2);
+    float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
+    fir_span<P, IN16, M, 0>(prm, sp, p, [&](int ii, long long i, float2 v) {
+      const unsigned sl = tile & 1;
+      // slot sl was last used by tile-2: every CTA has finished that FFT once the barrier it arrived at
+      // after it completes (first tiles: nothing to wait for)
+      if (ii == 0 && tile >= 2) cluster_wait_plain();
+      const unsigned dst = (unsigned)ii / RPC;          // CTA that transforms this row
+      const unsigned row_off = ((unsigned)ii % RPC) * (unsigned)(S * sizeof(float2));
+      st_async_f2(mapa_u32(in_addr[sl] + row_off + pos, dst), v, mapa_u32(full_addr[sl], dst));
+      if (ii == P - 1) {
+        const long long i0 = i - (P - 1) + rank * RPC; // first span row this CTA transforms
+        const long long left = sp.count - i0;
+        const int vhi = (int)(left < RPC ? (left < 0 ? 0 : left) : RPC);
+        const int vlo = i0 < sp.skip ? (int)(sp.skip - i0) : 0;
+        if (pend) {
+          fft_tile(pend_n, pend_gout, pend_vlo, pend_vhi);
+          cluster_arrive_relaxed();                    // this CTA is done with tile pend_n's slot
+        }
+        pend = true; pend_n = tile; pend_gout = gout + i0 * rstride; pend_vlo = vlo; pend_vhi = vhi;
+        tile++;
+      }
+    });
+  }
+  if (pend) {
+    // a wait is still owed for every arrive whose matching wait was never reached (at most one)
+    if (tile >= 2) cluster_wait_plain();
+    fft_tile(pend_n, pend_gout, pend_vlo, pend_vhi);
+  }
+  cluster_barrier();                                   // nobody leaves while a peer may still send to it or wait for it
 }
 
 // ---- M = 1024 fused on CTA pairs: decimation-in-time split over distributed shared memory ----------

@@ -108,6 +108,9 @@ def test_channelizer_matches_oracle(orc, M, P, os_, kind, n):
                                           (4096, 16, 1, 3), (2048, 16, 2, 3), (1024, 8, 1, 3), (64, 16, 1, 4), (64, 16, 2, 4), (64, 12, 1, 4), (64, 8, 2, 4),
                                           (1024, 16, 1, 5), (1024, 16, 2, 5), (1024, 12, 2, 5), (1024, 8, 1, 5),
                                           (4096, 16, 1, 6), (2048, 16, 2, 6), (1024, 8, 1, 6), (1024, 12, 2, 6), (1024, 16, 2, 6), (2048, 12, 1, 6),
+                                          (1024, 16, 2, 7), (2048, 16, 1, 7), (4096, 16, 1, 7), (1024, 16, 1, 7),
+                                          (1024, 16, 2, 10), (2048, 16, 1, 10), (4096, 16, 1, 10), (1024, 16, 1, 10), (2048, 16, 2, 10), (4096, 16, 2, 10),
+                                          (1024, 16, 2, 8), (2048, 16, 1, 8), (4096, 16, 1, 8), (1024, 16, 1, 8), (4096, 16, 2, 9), (1024, 8, 1, 9), (2048, 16, 1, 9),
                                           (56, 12, 1, 1), (56, 16, 2, 1), (56, 8, 1, 1), (56, 12, 2, 2), (560, 12, 1, 1), (560, 16, 2, 1), (560, 8, 1, 1), (560, 12, 2, 2)])
 def test_random_taps_every_tap_index_matters(orc, M, P, os_, path):
     """A designed prototype has tiny end taps, which would hide a mis-indexed tap or window slot
