@@ -248,7 +248,20 @@ __device__ __forceinline__ void fft_tile_to_global(float2* buf0, float2* buf1, c
                                                    SyncF sync) {
   typedef Plan<M> PL;
   if constexpr (PL::np == 1) {
-    stockham_pass<M, PL::r0, 1, ROWS, NT, true, false>(buf0, buf1, tw, twr, t, gout, grow_stride, vlo, vhi);
+    // M = 8, 16: one butterfly IS a whole row, so a thread that stored its own results would write 8-byte
+    // pieces of 32 different rows per instruction (partial sectors: 4x the L1->L2 write traffic; measured
+    // 40 % / 29 % of the HBM roofline).  The rows go through buf1 instead and are written out with the
+    // lanes across channels: every instruction stores whole 64- or 128-byte rows.
+    stockham_pass<M, PL::r0, 1, ROWS, NT, false, false>(buf0, buf1, tw, twr, t, gout, grow_stride, vlo, vhi);
+    sync();
+    constexpr int S = RowStride<M>::value;
+    #pragma unroll
+    for (int e0 = 0; e0 < ROWS * M; e0 += NT) {
+      const int e = e0 + t;
+      if ((ROWS * M) % NT != 0 && e >= ROWS * M) break;
+      const int row = e / M, i = e % M;
+      if (row >= vlo && row < vhi) gout[(long long)row * grow_stride + i] = buf1[row * S + padi<M>(i)];
+    }
   } else if constexpr (PL::np == 2) {
     stockham_pass<M, PL::r0, 1, ROWS, NT, false, false>(buf0, buf1, tw, twr, t, gout, grow_stride, vlo, vhi);
     sync();
