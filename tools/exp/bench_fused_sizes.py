@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import torch
 import sdr_channelizer_b200 as pkg
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-for M in (8, 16, 32, 56, 64, 128, 256, 512, 560):
+for M in [int(m) for m in os.environ.get("CHZ_BENCH_MS", "8,16,32,56,64,128,256,512,560").split(",")]:
     n = 560_000_000 // M * M
     x = torch.randint(-2000, 2000, (n, 2), dtype=torch.int16, device="cuda")
     rows = n // M
