@@ -274,7 +274,12 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": _traffic_from_profiles(), "kernel": "k_chan_fused<64,16,int16>",
                 "algorithmic_bytes_per_launch": shard.samples * BYTES_PER_SAMPLE_ALGO,
-                "ms_per_launch": kern_ms, "ms_per_launch_min": min(per_step_ms), "peak_source": peak_src}
+                "ms_per_launch": kern_ms, "ms_per_launch_min": min(per_step_ms),
+                "ms_per_launch_median": statistics.median(per_step_ms), "peak_source": peak_src}
+    if os.environ.get("CHZ_BENCH_DUMP"):      # per-step series (power-cap / clock drift diagnosis)
+        k = max(1, len(per_step_ms) // 10)
+        print("per-step ms, means of consecutive tenths:", [round(statistics.mean(per_step_ms[i:i + k]), 4) for i in range(0, len(per_step_ms), k)],
+              file=sys.stderr, flush=True)
 
     # end to end through the C ABI with HOST buffers: pinned input -> H2D -> kernels -> D2H -> pinned output
     e2e = None
