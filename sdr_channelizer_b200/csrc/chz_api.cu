@@ -776,7 +776,7 @@ void chz_destroy(chz_t* h) {
   h->cluster_ring.release();
   h->pipe_ctrl.release();
   for (int i = 0; i < 4; i++) { if (h->ev_fir[i]) cudaEventDestroy(h->ev_fir[i]); if (h->ev_fft[i]) cudaEventDestroy(h->ev_fft[i]); }
-  for (chzi::Scratch* sc : {&h->pdw_hist, &h->pdw_sel, &h->pdw_thr, &h->pdw_cnt, &h->pdw_ev, &h->pdw_pin, &h->pdw_pout, &h->pdw_code}) sc->release();
+  for (chzi::Scratch* sc : {&h->pdw_hist, &h->pdw_sel, &h->pdw_thr, &h->pdw_cnt, &h->pdw_ev, &h->pdw_pin, &h->pdw_pout, &h->pdw_code, &h->pdw_nf}) sc->release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);

@@ -126,6 +126,33 @@ __global__ void __launch_bounds__(256) k_select(uint32_t* __restrict__ hist, Sel
 // hysteresis (create_pdws.m:45-47,58,63: 18 dB up, 3 dB down => le < ge).
 struct Thr { float ge, le; };
 
+// Noise floor and thresholds (:73-75) from the selected order statistics, in double like the script, then
+// bracketed by floats: ge = smallest float >= T_lead, le = largest float <= T_trail (so the fp32 comparisons
+// of k_detect decide exactly like the double comparison would).  On the device so that the extractor does
+// not have to stop for a round trip through the host between the median and the edge detector.
+__device__ __forceinline__ float float_ge(double t) {
+  float f = __double2float_rn(t);
+  if ((double)f < t) f = f == 0.f ? __uint_as_float(1u) : (f > 0.f ? __uint_as_float(__float_as_uint(f) + 1u) : __uint_as_float(__float_as_uint(f) - 1u));
+  return f;
+}
+__device__ __forceinline__ float float_le(double t) {
+  float f = __double2float_rn(t);
+  if ((double)f > t) f = f == 0.f ? __uint_as_float(0x80000001u) : (f > 0.f ? __uint_as_float(__float_as_uint(f) - 1u) : __uint_as_float(__float_as_uint(f) + 1u));
+  return f;
+}
+__global__ void k_thresholds(const SelState* __restrict__ st, int M, double scale, double scale_lo, Thr* __restrict__ thr,
+                             double* __restrict__ nf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= M) return;
+  const double lo = (double)__uint_as_float(st[k].prefix[0]), hi = (double)__uint_as_float(st[k].prefix[1]);
+  const double v = 0.5 * (lo + hi);                      // MATLAB median: mean of the two middle values
+  nf[k] = v;
+  Thr t;
+  t.ge = float_ge(v * scale);
+  t.le = float_le(v * scale_lo);
+  thr[k] = t;
+}
+
 // Lanes walk channels (coalesced 8-byte loads of a row), all lanes advance row by row through the same
 // chunk, so a warp ballot per row tells whether any channel saw an edge; one atomic per warp reserves
 // the slots and every lane with an edge writes at its ballot rank.
@@ -324,6 +351,7 @@ static int pdw_buffers(::chz* h) {
   CHZ_CUDA(h->pdw_thr.reserve((size_t)M * sizeof(Thr)));
   CHZ_CUDA(h->pdw_cnt.reserve(sizeof(unsigned long long)));
   CHZ_CUDA(h->pdw_code.reserve((size_t)M));
+  CHZ_CUDA(h->pdw_nf.reserve((size_t)M * sizeof(double)));
   (void)fresh;
   return CHZ_OK;
 }
@@ -359,44 +387,45 @@ static int pdw_select_pass(::chz* h, int pass, uint64_t total_rows) {
   return CHZ_OK;
 }
 
-// noise floor and thresholds (:73-75), double on the host, bracketed by floats for the fp32 comparisons
-static int pdw_thresholds(::chz* h, const chz_pdw_params_t* prm) {
+// noise floor and thresholds (:73-75) on the device (k_thresholds).  fetch: also bring the noise floor to
+// h->noise_floor now (one synchronisation); otherwise the caller copies it with its next transfer.
+static int pdw_thresholds(::chz* h, const chz_pdw_params_t* prm, bool fetch) {
   const int M = (int)h->M;
   cudaStream_t st = h->stream;
-  std::vector<SelState> sel(M);
-  CHZ_CUDA(cudaMemcpyAsync(sel.data(), h->pdw_sel.p, sizeof(SelState) * M, cudaMemcpyDeviceToHost, st));
-  CHZ_CUDA(cudaStreamSynchronize(st));
   const double scale = std::pow(10.0, prm->snr_threshold_db / 10.0);
   // create_pdws.m:47: TRAILING_EDGE_THRESHOLD = NOISE_FLOOR*10^(3/10); never above the leading threshold
   const bool hyst = prm->use_trailing_threshold != 0 && prm->trailing_snr_threshold_db < prm->snr_threshold_db;
   const double scale_lo = hyst ? std::pow(10.0, prm->trailing_snr_threshold_db / 10.0) : scale;
-  auto float_ge = [](double t) { float f = (float)t; return (double)f < t ? std::nextafterf(f, INFINITY) : f; };
-  auto float_le = [](double t) { float f = (float)t; return (double)f > t ? std::nextafterf(f, -INFINITY) : f; };
-  std::vector<Thr> thr(M);
+  k_thresholds<<<(M + 127) / 128, 128, 0, st>>>((const SelState*)h->pdw_sel.p, M, scale, scale_lo, (Thr*)h->pdw_thr.p,
+                                                (double*)h->pdw_nf.p);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
   h->noise_floor.assign(M, NAN);
-  for (int k = 0; k < M; k++) {
-    float lo, hi;
-    memcpy(&lo, &sel[k].prefix[0], 4);
-    memcpy(&hi, &sel[k].prefix[1], 4);
-    const double nf = 0.5 * ((double)lo + (double)hi);     // MATLAB median: mean of the two middle values
-    h->noise_floor[k] = nf;
-    thr[k].ge = float_ge(nf * scale);
-    thr[k].le = float_le(nf * scale_lo);
+  if (fetch) {
+    CHZ_CUDA(cudaMemcpyAsync(h->noise_floor.data(), h->pdw_nf.p, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+    CHZ_CUDA(cudaStreamSynchronize(st));
   }
-  CHZ_CUDA(cudaMemcpyAsync(h->pdw_thr.p, thr.data(), sizeof(Thr) * M, cudaMemcpyHostToDevice, st));
-  CHZ_CUDA(cudaStreamSynchronize(st));   // thr lives on this stack frame
   return CHZ_OK;
 }
 
 // edge events (:79-96) of y[nrows][M]; rows in the events are 1-based and offset by row_offset;
-// entry_host: per natural channel state on entry (NULL = inactive)
+// entry_host: per natural channel state on entry (NULL = inactive).  The event counter sits at the head of
+// the device event buffer so that one transfer brings the count and (normally) every event; nf_fetch: the
+// noise floor rides along in front of the same synchronisation.
 static int pdw_detect(::chz* h, const float2* y, uint64_t nrows, uint64_t row_offset, const uint8_t* entry_host,
-                      std::vector<unsigned long long>& ev) {
+                      std::vector<unsigned long long>& ev, bool nf_fetch) {
   const int M = (int)h->M;
   cudaStream_t st = h->stream;
   ev.clear();
-  if (nrows == 0) return CHZ_OK;
-  unsigned long long* d_cnt = (unsigned long long*)h->pdw_cnt.p;
+  auto fetch_nf = [&]() -> int {   // after the launches: a copy to pageable memory may block the host
+    if (nf_fetch) CHZ_CUDA(cudaMemcpyAsync(h->noise_floor.data(), h->pdw_nf.p, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+    return CHZ_OK;
+  };
+  if (nrows == 0) {
+    if (fetch_nf()) return CHZ_ECUDA;
+    CHZ_CUDA(cudaStreamSynchronize(st));
+    return CHZ_OK;
+  }
   uint8_t* d_entry = nullptr;
   if (entry_host) {
     d_entry = (uint8_t*)h->pdw_code.p;
@@ -407,22 +436,28 @@ static int pdw_detect(::chz* h, const float2* y, uint64_t nrows, uint64_t row_of
   const int lanes_ch = M < 32 ? M : 32, streams = 32 / lanes_ch, ch_groups = (M + 31) / 32;
   const long long warps = ((nchunks + streams - 1) / streams) * ch_groups;
   const long long blocks = (warps + 7) / 8;
-  unsigned long long nev = 0;
+  constexpr unsigned long long kFirst = 8191;   // events fetched together with the count (64 KB)
   for (;;) {
     const unsigned long long cap = h->pdw_ev_cap;
-    CHZ_CUDA(h->pdw_ev.reserve(cap * sizeof(unsigned long long)));
-    unsigned long long* d_ev = (unsigned long long*)h->pdw_ev.p;
+    CHZ_CUDA(h->pdw_ev.reserve((cap + 1) * sizeof(unsigned long long)));
+    unsigned long long* d_cnt = (unsigned long long*)h->pdw_ev.p;
+    unsigned long long* d_ev = d_cnt + 1;
     CHZ_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
     k_detect<<<(unsigned)blocks, 256, 0, st>>>(y, (long long)nrows, M, (const Thr*)h->pdw_thr.p, chunk_rows, d_entry,
                                                (unsigned long long)row_offset, d_ev, cap, d_cnt);
     h->launches++;
     CHZ_CUDA(cudaGetLastError());
-    CHZ_CUDA(cudaMemcpyAsync(&nev, d_cnt, sizeof nev, cudaMemcpyDeviceToHost, st));
+    if (fetch_nf()) return CHZ_ECUDA;
+    const unsigned long long first = cap < kFirst ? cap : kFirst;
+    ev.resize(first + 1);
+    CHZ_CUDA(cudaMemcpyAsync(ev.data(), d_cnt, (first + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CHZ_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long nev = ev[0];
     if (nev <= cap) {
+      ev.erase(ev.begin());
       ev.resize(nev);
-      if (nev) {
-        CHZ_CUDA(cudaMemcpyAsync(ev.data(), d_ev, nev * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      if (nev > first) {
+        CHZ_CUDA(cudaMemcpyAsync(ev.data() + first, d_ev + first, (nev - first) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CHZ_CUDA(cudaStreamSynchronize(st));
       }
       break;
@@ -526,10 +561,10 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
   }
   lap("median");
   // 2. thresholds (:74-75)
-  if ((rc = pdw_thresholds(h, prm))) return rc;
-  // 3. edge events (:79-96)
+  if ((rc = pdw_thresholds(h, prm, false))) return rc;
+  // 3. edge events (:79-96); the noise floor comes back with the event count
   std::vector<unsigned long long> ev;
-  if ((rc = pdw_detect(h, y, nrows, 0, nullptr, ev))) return rc;
+  if ((rc = pdw_detect(h, y, nrows, 0, nullptr, ev, true))) return rc;
   lap("detect");
   // 4. pulses in the reference's order: shifted channel ascending, then time
   std::vector<chz_pulse_t> pulses;
@@ -575,7 +610,7 @@ int chz_pdw_shard_thresholds(chz_t* h, const chz_pdw_params_t* params) {
   if (!h || !params || !h->pdw_sel.p) return CHZ_EINVAL;
   CHZ_CUDA(cudaSetDevice(h->device));
   h->pdws.clear();
-  return pdw_thresholds(h, params);
+  return pdw_thresholds(h, params, true);
 }
 
 int chz_pdw_shard_exit_state_dev(chz_t* h, const chz_cf32* y_dev, uint64_t nrows, uint8_t* code) {
@@ -598,7 +633,7 @@ int chz_pdw_shard_detect_dev(chz_t* h, const chz_cf32* y_dev, uint64_t nrows, ui
   if (row_offset + nrows >= (1ull << 39)) return CHZ_EINVAL;
   CHZ_CUDA(cudaSetDevice(h->device));
   std::vector<unsigned long long> ev;
-  const int rc = pdw_detect(h, (const float2*)y_dev, nrows, row_offset, entry, ev);
+  const int rc = pdw_detect(h, (const float2*)y_dev, nrows, row_offset, entry, ev, false);
   if (rc) return rc;
   *n = ev.size();
   if (ev.size() > cap) return CHZ_ECAPACITY;
