@@ -239,6 +239,18 @@ int chz_pdw_pair_events(uint64_t* events, uint64_t n, uint32_t M, uint32_t repro
 int chz_pdw_shard_records_dev(chz_t* h, const chz_pdw_params_t* params, const chz_cf32* y_dev, uint64_t ld,
                               uint64_t row_offset, const chz_pulse_t* pulses, uint64_t n, chz_pdw_t* out);
 
+/* ---- event prediction from PDWs (host only) --------------------------------------------------------
+ * The analysis the reference runs on the extractor's output (matlab/predict_event.m:125-138,
+ * cpp/usrp_predict_event.cpp:28-52,348-373). */
+/* Quadratic least-squares fit v ~ c0 + c1 t + c2 t^2 over n >= 3 points (Householder QR of [1 t t^2], i.e.
+ * polyfit(pdw.toa, pdw.snr, 2), predict_event.m:125); *t_peak = -c1/(2 c2) (:128), *v_peak = the fit there
+ * (:129); coef (optional) receives c0, c1, c2.  CHZ_EINVAL when the fit is rank deficient or has no peak. */
+int chz_event_peak_time(const double* t, const double* v, uint64_t n, double* t_peak, double* v_peak, double* coef);
+/* last event + median of the differences of successive event times (:133-135); one event: + fallback_interval
+ * (:137).  upper_median != 0 takes element [size/2] of the sorted differences like the C++ tool
+ * (usrp_predict_event.cpp:364-368) instead of MATLAB's median. */
+int chz_next_event_time(const double* events, uint64_t n, double fallback_interval, int upper_median, double* next);
+
 /* Device pointer and row count of the retained store (for callers that keep working on the GPU). */
 int chz_retained(const chz_t* h, const chz_cf32** y_dev, uint64_t* nrows);
 int chz_reserve_rows(chz_t* h, uint64_t nrows);

@@ -195,3 +195,17 @@ def median(v):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+# ---- event prediction (matlab/predict_event.m:125-138), numpy restatement ------------------------------
+def event_peak_time(toa, snr):
+    """p = polyfit(pdw.toa, pdw.snr, 2) (:125); t_max = -p(2)/(2*p(1)) (:128); y_max (:129)."""
+    p = np.polyfit(np.asarray(toa, dtype=np.float64), np.asarray(snr, dtype=np.float64), 2)
+    t_max = -p[1] / (2 * p[0])
+    return t_max, p[0] * t_max ** 2 + p[1] * t_max + p[2]
+
+
+def next_event_time(events, fallback_interval=4.61962892466417):
+    """:133-138: median(diff(event)) + t_max, or t_max + 4.6196... for the first event."""
+    e = np.asarray(events, dtype=np.float64)
+    return e[-1] + (np.median(np.diff(e)) if len(e) > 1 else fallback_interval)

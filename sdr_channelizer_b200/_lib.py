@@ -25,6 +25,7 @@ EXPORTS = [
     "chz_kernel_launches", "chz_alloc_host", "chz_free_host",
     "chz_pdw_shard_hist_dev", "chz_pdw_shard_select", "chz_pdw_shard_thresholds", "chz_pdw_shard_exit_state_dev",
     "chz_pdw_shard_detect_dev", "chz_pdw_pair_events", "chz_pdw_shard_records_dev",
+    "chz_event_peak_time", "chz_next_event_time",
 ]
 
 
@@ -119,6 +120,8 @@ def lib():
     L.chz_pdw_shard_detect_dev.argtypes = [vp, vp, u64, u64, vp, vp, u64, pu64]; L.chz_pdw_shard_detect_dev.restype = i32
     L.chz_pdw_pair_events.argtypes = [vp, u64, u32, u32, vp, u64, pu64]; L.chz_pdw_pair_events.restype = i32
     L.chz_pdw_shard_records_dev.argtypes = [vp, C.POINTER(PdwParams), vp, u64, u64, vp, u64, vp]; L.chz_pdw_shard_records_dev.restype = i32
+    L.chz_event_peak_time.argtypes = [vp, vp, u64, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]; L.chz_event_peak_time.restype = i32
+    L.chz_next_event_time.argtypes = [vp, u64, C.c_double, i32, C.POINTER(C.c_double)]; L.chz_next_event_time.restype = i32
     L.chz_alloc_host.argtypes = [u64]; L.chz_alloc_host.restype = vp
     L.chz_free_host.argtypes = [vp]; L.chz_free_host.restype = None
     _lib = L

@@ -307,5 +307,64 @@ def create_pdws(recordings, SNR_THRESHOLD=18.0, TRAILING_EDGE_THRESHOLD=3.0):
     return {k: np.asarray(v) for k, v in out.items()}
 
 
+def event_peak_time(toa, snr):
+    """p = polyfit(toa, snr, 2); t_max = -p(2)/(2 p(1)); y_max = polyval(p, t_max)
+    (matlab/predict_event.m:125-129, cpp/usrp_predict_event.cpp:28-52).  -> (t_max, y_max, (c0, c1, c2))."""
+    t = np.ascontiguousarray(toa, dtype=np.float64)
+    v = np.ascontiguousarray(snr, dtype=np.float64)
+    tp, vp = C.c_double(0), C.c_double(0)
+    coef = np.zeros(3, dtype=np.float64)
+    check(lib().chz_event_peak_time(t.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), len(t), C.byref(tp),
+                                    C.byref(vp), coef.ctypes.data_as(C.c_void_p)), "chz_event_peak_time")
+    return tp.value, vp.value, tuple(coef)
+
+
+def next_event_time(events, fallback_interval=4.61962892466417, upper_median=False):
+    """median(diff(event)) + t_max, or t_max + the script's fixed interval for the first event
+    (predict_event.m:133-138); upper_median=True is the C++ tool's median (usrp_predict_event.cpp:364-368)."""
+    e = np.ascontiguousarray(events, dtype=np.float64)
+    nxt = C.c_double(0)
+    check(lib().chz_next_event_time(e.ctypes.data_as(C.c_void_p), len(e), float(fallback_interval), int(bool(upper_median)),
+                                    C.byref(nxt)), "chz_next_event_time")
+    return nxt.value
+
+
+def predict_event(recordings, SNR_THRESHOLD=20.0, min_peak=0.9):
+    """matlab/predict_event.m as a function.  For every recording whose normalised peak magnitude exceeds 0.9
+    (:52) extract wideband PDWs with one 20 dB threshold over the median magnitude (:63-65,76-83; TOAs relative
+    to the first recording's sampleStartTime, :88), fit SNR against TOA with a parabola and take its vertex as
+    the event time (:125-131), then predict the next event from the median spacing (:133-138).
+    Returns dict(event, next_event, y_max, pdws_per_file)."""
+    out = {"event": [], "next_event": [], "y_max": [], "pdws_per_file": []}
+    first = None
+    for rec in recordings:
+        if not isinstance(rec, IqRecording):
+            rec = read_iq(rec)
+        if first is None:
+            first = rec.sampleStartTime                                   # :46-48
+        iq = np.ascontiguousarray(rec.iq)
+        full = float(2 ** (rec.bitWidth - 1))
+        peak2 = int(np.max(iq[:, 0].astype(np.int64) ** 2 + iq[:, 1].astype(np.int64) ** 2)) if len(iq) else 0
+        if not peak2 > (min_peak * full) ** 2:                             # :52  max(abs(iq)) > 0.9
+            out["pdws_per_file"].append(0)
+            continue
+        ch = Channelizer(1, taps=np.ones(1, dtype=np.float32))
+        try:
+            n = C.c_uint64(0)
+            check(lib().chz_process(ch.handle, iq.ctypes.data_as(C.c_void_p), iq.shape[0], rec.bitWidth,
+                                    None, 0, C.byref(n)), "chz_process")
+            recs, _ = ch.pdws(rec.fs, rec.fc, rec.sampleStartTime - first, SNR_THRESHOLD)   # :63-123
+        finally:
+            ch.close()
+        out["pdws_per_file"].append(len(recs))
+        if len(recs) < 3:
+            continue
+        t_max, y_max, _ = event_peak_time([r.toa_s for r in recs], [r.snr_db for r in recs])   # :125-129
+        out["event"].append(t_max)                                                               # :131
+        out["y_max"].append(y_max)
+        out["next_event"].append(next_event_time(out["event"]))                                  # :133-138
+    return {k: np.asarray(v) for k, v in out.items()}
+
+
 __all__ = ["IqRecording", "read_iq", "write_iq", "design_prototype", "Channelizer", "unpack_ptr",
-           "create_pdws_channelized", "create_pdws", "ChannelizerError"]
+           "create_pdws_channelized", "create_pdws", "predict_event", "event_peak_time", "next_event_time", "ChannelizerError"]

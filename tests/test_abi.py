@@ -133,3 +133,31 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in text.lower() or f == "__init__.py" and False, os.path.join(dirpath, f)
+
+
+# ---- host-only entry points: event prediction (matlab/predict_event.m:125-138) -------------------------
+def test_event_peak_time_against_numpy_polyfit(orc):
+    import sdr_channelizer_b200 as pkg
+    rng = np.random.default_rng(3)
+    t = np.sort(rng.uniform(0.0, 9.0, 40))
+    v = 22.0 - 0.8 * (t - 4.25) ** 2 + rng.normal(0, 0.2, t.size)
+    tp, vp, coef = pkg.event_peak_time(t, v)
+    otp, ovp = orc.event_peak_time(t, v)
+    assert abs(tp - otp) < 1e-9 and abs(vp - ovp) < 1e-9
+    assert np.allclose(coef[::-1], np.polyfit(t, v, 2), rtol=1e-9, atol=1e-9)
+    # an exact parabola is recovered exactly (to rounding)
+    tp, vp, _ = pkg.event_peak_time(t, 5.0 - 2.0 * (t - 3.0) ** 2)
+    assert abs(tp - 3.0) < 1e-10 and abs(vp - 5.0) < 1e-9
+    for bad_t, bad_v in (([1.0, 2.0], [1.0, 2.0]), ([1.0, 1.0, 1.0, 1.0], [1.0, 2.0, 3.0, 4.0]), ([0.0, 1.0, 2.0, 3.0], [0.0, 1.0, 2.0, 3.0])):
+        with pytest.raises(pkg.ChannelizerError):      # too few points / rank deficient / no curvature
+            pkg.event_peak_time(bad_t, bad_v)
+
+
+def test_next_event_time_median_rules(orc):
+    import sdr_channelizer_b200 as pkg
+    ev = [10.0, 14.5, 19.2, 23.7, 28.6]                 # differences 4.5 4.7 4.5 4.9 -> median 4.6
+    assert abs(pkg.next_event_time(ev) - orc.next_event_time(ev)) < 1e-12
+    assert abs(pkg.next_event_time(ev) - (28.6 + 4.6)) < 1e-12
+    assert abs(pkg.next_event_time(ev, upper_median=True) - (28.6 + 4.7)) < 1e-12     # usrp_predict_event.cpp:366
+    assert abs(pkg.next_event_time(ev[:4]) - (23.7 + 4.5)) < 1e-12                     # odd count: the middle one
+    assert pkg.next_event_time([7.0]) == 7.0 + 4.61962892466417                        # predict_event.m:137

@@ -262,3 +262,46 @@ def test_sharded_pdws_pulsed_recording_and_phase_bug():
         for recs, nfs in _sharded_on_one_gpu(y, bounds, fs, **kw):
             _same_records(recs, whole)
             assert np.array_equal(nfs, nf)
+
+
+# ---- event prediction (matlab/predict_event.m) ---------------------------------------
+def _event_recording(seed, fs, n, t_peak, nf=0.004):
+    """A dwell in which a pulsed emitter sweeps past: pulse amplitudes follow a parabola in dB that peaks
+    at t_peak seconds into the file; one pulse reaches 0.95 of full scale so the script's gate (:52) opens."""
+    rng = np.random.default_rng(seed)
+    x = (rng.normal(0, nf, n) + 1j * rng.normal(0, nf, n)).astype(np.complex128)
+    pri, pw = int(fs * 2e-3), int(fs * 60e-6)
+    for a in range(pri // 2, n - pw, pri):
+        tc = (a + pw / 2) / fs
+        amp = 0.95 * 10.0 ** (-(40.0 * (tc - t_peak) ** 2) / 10.0)       # power-dB law, as the script's SNR (:95)
+        x[a:a + pw] += amp * np.exp(2j * np.pi * 0.03 * np.arange(pw))
+    return np.stack([np.clip(np.rint(x.real * 32768), -32768, 32767), np.clip(np.rint(x.imag * 32768), -32768, 32767)],
+                    axis=1).astype(np.int16)
+
+
+def test_predict_event_script_against_oracle(orc, tmp_path):
+    """predict_event.m end to end on three dwells 4.5 s apart (plus one quiet dwell the :52 gate skips): PDWs with
+    a single 20 dB threshold, parabola fit of SNR vs TOA, vertex = event time, next event from the median
+    spacing -- against the oracle's PDWs + numpy.polyfit."""
+    _torch()
+    fs, n = 2e6, 200_000                                                  # 100 ms dwells
+    starts = [1000.0, 1004.5, 1007.0, 1009.1]
+    peaks = [0.047, 0.052, None, 0.044]
+    paths, oevents = [], []
+    for i, (t0, tp) in enumerate(zip(starts, peaks)):
+        iq = _event_recording(40 + i, fs, n, tp) if tp is not None else (_event_recording(40 + i, fs, n, 0.05) // 8).astype(np.int16)
+        p = str(tmp_path / f"dwell{i}.iq")
+        pkg.write_iq(p, iq, fs=fs, fc=1.3e9, bitWidth=16, sampleStartTime=t0)
+        paths.append(p)
+        y = orc.unpack(iq, 16).reshape(-1, 1)
+        if np.max(np.abs(y)) > 0.9:                                       # :52
+            orecs, _ = orc.pdws(y, 1, snr_threshold_db=20.0, fc_hz=1.3e9, fs_sps=fs, t0=t0 - starts[0])
+            oevents.append(orc.event_peak_time([r.toa_s for r in orecs], [r.snr_db for r in orecs])[0])
+    res = pkg.predict_event(paths)
+    assert res["pdws_per_file"][2] == 0 and all(c > 20 for i, c in enumerate(res["pdws_per_file"]) if i != 2)
+    assert len(res["event"]) == len(oevents) == 3
+    assert np.allclose(res["event"], oevents, atol=1e-6)
+    for ev, t0, tp in zip(res["event"], [s for s, p in zip(starts, peaks) if p is not None], [p for p in peaks if p is not None]):
+        assert abs(ev - (t0 - starts[0] + tp)) < 2e-3                     # the vertex sits where the emitter peaked
+    assert abs(res["next_event"][0] - (res["event"][0] + 4.61962892466417)) < 1e-12
+    assert abs(res["next_event"][-1] - orc.next_event_time(oevents)) < 1e-6
