@@ -226,7 +226,7 @@ __global__ void k_fir_any(ChanParams prm, int P, float2* __restrict__ u) {
 // Any-M row DFT (the reference's natural channel counts are not powers of two: M = fs*1e-6 = 56,
 // matlab/create_pdws_channelized.m:31).  Direct evaluation y_k = sum_p u_p W_M^{kp}, O(M^2) per row,
 // table W_M^i in shared memory indexed by (k p) mod M.  Functional path, not tuned.
-__global__ void __launch_bounds__(256) k_dft_rows_any(const float2* u, float2* y, const float2* __restrict__ tw_g, int M,
+static __global__ void __launch_bounds__(256) k_dft_rows_any(const float2* u, float2* y, const float2* __restrict__ tw_g, int M,
                                                       long long nrows) {
   extern __shared__ float2 smem[];
   float2* row = smem;

@@ -345,14 +345,11 @@ __global__ void __launch_bounds__(128) k_pulse_stats(const float2* __restrict__ 
 // the host sums the histograms of all shards between hist and select).
 static int pdw_buffers(::chz* h) {
   const int M = (int)h->M;
-  const bool fresh = h->pdw_hist.bytes < (size_t)M * 2 * kBins * sizeof(uint32_t);
   CHZ_CUDA(h->pdw_hist.reserve((size_t)M * 2 * kBins * sizeof(uint32_t)));
   CHZ_CUDA(h->pdw_sel.reserve((size_t)M * sizeof(SelState)));
   CHZ_CUDA(h->pdw_thr.reserve((size_t)M * sizeof(Thr)));
-  CHZ_CUDA(h->pdw_cnt.reserve(sizeof(unsigned long long)));
   CHZ_CUDA(h->pdw_code.reserve((size_t)M));
   CHZ_CUDA(h->pdw_nf.reserve((size_t)M * sizeof(double)));
-  (void)fresh;
   return CHZ_OK;
 }
 
