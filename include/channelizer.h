@@ -93,8 +93,9 @@ typedef struct chz chz_t;
 typedef struct chz_cf32 { float re, im; } chz_cf32;
 
 /* M: 1..4096.  M = 1 with the single tap 1.0 is the identity "channelizer" (unpack only), which
- * makes chz_pdws the wideband extractor of matlab/create_pdws.m.  Powers of two >= 8 run the tuned kernels; any other M (the reference's natural
- * M = fs*1e-6 = 56, create_pdws_channelized.m:31) runs a functional direct-FIR + O(M^2) DFT path.
+ * makes chz_pdws the wideband extractor of matlab/create_pdws.m.  Powers of two >= 8 and the reference's own
+ * M = fs*1e-6 = 56 (create_pdws_channelized.m:31) and 560 run the tuned fused kernels; any other M with prime
+ * factors <= 7 runs a split path with a run-time mixed-radix FFT; the rest a functional O(M^2) DFT path.
  * ntaps: positive multiple of M, ntaps/M <= 32; oversample 1 (D = M, critically sampled) or 2
  * (D = M/2, M even).  taps == NULL -> default prototype (12*M taps, 80 dB;
  * ntaps is then ignored).  Taps are copied. */

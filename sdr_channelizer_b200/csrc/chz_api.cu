@@ -47,7 +47,8 @@ LaunchPlan plan_spans(const ::chz* h, long long nrows, int P, int groups_per_blo
 
 template <int P, bool IN16, int MT>
 static int launch_fir_m(::chz* h, ChanParams prm, float2* u, cudaStream_t st) {
-  const int bpb = prm.M < 128 ? prm.M : (prm.M % 128 == 0 ? 128 : 112), nbb = prm.M / bpb, groups = 128 / bpb;   // as in k_fir
+  const int bpb = MT ? (MT < 128 ? MT : 128) : h->fir_bpb, nbb = prm.M / bpb, groups = 128 / bpb;   // as in k_fir
+  prm.bpb = bpb;
   // 128 threads x <= 128 registers: 4 blocks resident per SM; span blocks per branch block = SMs*4 / nbb
   LaunchPlan lp = plan_spans(h, prm.nrows, P, groups, 4, (h->sm_count * 4 / nbb) > 0 ? (h->sm_count * 4 / nbb) : 1);
   prm.span_rows = lp.span_rows;
@@ -116,6 +117,29 @@ static int launch_fft_rows_big(::chz* h, const float2* u, float2* y, long long n
 }
 
 static int launch_fft_rows(::chz* h, const float2* u, float2* y, long long nrows, cudaStream_t st) {
+  if (h->generic && h->mixed_np > 0) {
+    if (nrows < 1) return CHZ_OK;
+    const int M = (int)h->M;
+    int rpb = 2048 / M;
+    if (rpb < 1) rpb = 1;
+    const size_t smem = (size_t)2 * rpb * M * sizeof(float2);
+    static thread_local bool attr_set_dev[kMaxDev] = {false};
+    bool& attr_set = attr_set_dev[h->device % kMaxDev];
+    if (!attr_set) {
+      CHZ_CUDA(cudaFuncSetAttribute(k_fft_rows_mixed, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * (int)sizeof(float2)));
+      attr_set = true;
+    }
+    MixedPlan plan;
+    plan.np = h->mixed_np;
+    for (int i = 0; i < 12; i++) plan.r[i] = h->mixed_r[i];
+    long long blocks = (nrows + rpb - 1) / rpb;
+    const long long maxb = (long long)h->sm_count * 6;
+    if (blocks > maxb) blocks = maxb;
+    k_fft_rows_mixed<<<(unsigned)blocks, 256, smem, st>>>(u, y, h->d_tw, M, nrows, rpb, plan);
+    h->launches++;
+    CHZ_CUDA(cudaGetLastError());
+    return CHZ_OK;
+  }
   if (h->generic) {
     if (nrows < 1) return CHZ_OK;
     const size_t smem = (size_t)2 * h->M * sizeof(float2);
@@ -150,7 +174,7 @@ static int launch_fft_rows(::chz* h, const float2* u, float2* y, long long nrows
 
 template <bool IN16>
 static int launch_fir_dispatch(::chz* h, const ChanParams& prm, float2* u, cudaStream_t st) {
-  switch (h->generic ? 0u : h->P) {
+  switch ((h->generic && h->fir_bpb == 0) ? 0u : h->P) {
     case 4: return launch_fir<4, IN16>(h, prm, u, st);
     case 8: return launch_fir<8, IN16>(h, prm, u, st);
     case 12: return launch_fir<12, IN16>(h, prm, u, st);
@@ -388,6 +412,33 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
   // no radix plan: direct FIR + O(M^2) row DFT kernels.  56 = 8*7 and 560 = 16*5*7, the reference's own
   // channel counts (create_pdws_channelized.m:31, generate_channelized_training_iq.m:95-96), have plans.
   h->generic = (M < 8 || (M & (M - 1)) != 0) && M != 56 && M != 560;
+  if (h->generic && M >= 2) {
+    // run-time mixed-radix plan when M = 2^a 3^b 5^c 7^d: 16s first, then 8/4/2, then 7, 5, 3 (larger radices first)
+    uint32_t m = M;
+    int c2 = 0, c3 = 0, c5 = 0, c7 = 0;
+    while (m % 2 == 0) { m /= 2; c2++; }
+    while (m % 3 == 0) { m /= 3; c3++; }
+    while (m % 5 == 0) { m /= 5; c5++; }
+    while (m % 7 == 0) { m /= 7; c7++; }
+    if (m == 1) {
+      int np = 0;
+      while (c2 >= 4) { h->mixed_r[np++] = 16; c2 -= 4; }
+      if (c2 == 3) h->mixed_r[np++] = 8;
+      if (c2 == 2) h->mixed_r[np++] = 4;
+      if (c2 == 1) h->mixed_r[np++] = 2;
+      for (int i = 0; i < c7; i++) h->mixed_r[np++] = 7;
+      for (int i = 0; i < c5; i++) h->mixed_r[np++] = 5;
+      for (int i = 0; i < c3; i++) h->mixed_r[np++] = 3;
+      std::sort(h->mixed_r, h->mixed_r + np, [](int a, int b) { return a > b; });
+      h->mixed_np = np;
+    }
+  }
+  // register-window FIR with run-time M: M branches per 128-thread block when they fit, else the largest
+  // divisor of M that does (none >= 32: the direct FIR kernel)
+  if (M <= 128) h->fir_bpb = (int)M;
+  else
+    for (uint32_t d = 128; d >= 32; d--)
+      if (M % d == 0) { h->fir_bpb = (int)d; break; }
   if (taps) {
     h->taps.assign(taps, taps + ntaps);
   } else {
@@ -410,24 +461,30 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
   // Inter-pass twiddles of the Stockham plan (same radices as Plan<M> on the device), laid out per pass
   // as entry (q-1)*NS + k = W_{NS R}^{q k} = e^{+j 2 pi q k / (NS R)} so a warp reads consecutive k.
   std::vector<float2> tw(M, make_float2(1.f, 0.f));
-  if (h->generic) {   // plain table W_M^i = e^{+j 2 pi i / M}
+  if (h->generic && h->mixed_np == 0) {   // plain table W_M^i = e^{+j 2 pi i / M} for the O(M^2) DFT
     for (uint32_t i = 0; i < M; i++) {
       const double a = 2.0 * 3.14159265358979323846264338327950288 * (double)i / (double)M;
       tw[i] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
   } else {
-    int r[3] = {1, 1, 1};
-    switch (M) {
-      case 8: r[0] = 8; break;              case 16: r[0] = 16; break;
-      case 32: r[0] = 8; r[1] = 4; break;   case 64: r[0] = 8; r[1] = 8; break;
-      case 128: r[0] = 16; r[1] = 8; break; case 256: r[0] = 16; r[1] = 16; break;
-      case 512: r[0] = 16; r[1] = 8; r[2] = 4; break;   case 1024: r[0] = 16; r[1] = 8; r[2] = 8; break;
-      case 2048: r[0] = 16; r[1] = 16; r[2] = 8; break; case 4096: r[0] = 16; r[1] = 16; r[2] = 16; break;
-      case 56: r[0] = 8; r[1] = 7; break;               case 560: r[0] = 16; r[1] = 5; r[2] = 7; break;
+    int r[12] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+    int np = 3;
+    if (h->generic) {
+      np = h->mixed_np;
+      for (int i = 0; i < np; i++) r[i] = h->mixed_r[i];
+    } else {
+      switch (M) {
+        case 8: r[0] = 8; break;              case 16: r[0] = 16; break;
+        case 32: r[0] = 8; r[1] = 4; break;   case 64: r[0] = 8; r[1] = 8; break;
+        case 128: r[0] = 16; r[1] = 8; break; case 256: r[0] = 16; r[1] = 16; break;
+        case 512: r[0] = 16; r[1] = 8; r[2] = 4; break;   case 1024: r[0] = 16; r[1] = 8; r[2] = 8; break;
+        case 2048: r[0] = 16; r[1] = 16; r[2] = 8; break; case 4096: r[0] = 16; r[1] = 16; r[2] = 16; break;
+        case 56: r[0] = 8; r[1] = 7; break;               case 560: r[0] = 16; r[1] = 5; r[2] = 7; break;
+      }
     }
     size_t off = 0;
     int ns = r[0];
-    for (int pass = 1; pass < 3 && r[pass] > 1; pass++) {
+    for (int pass = 1; pass < np && r[pass] > 1; pass++) {
       const int R = r[pass];
       for (int q = 1; q < R; q++)
         for (int k = 0; k < ns; k++) {

@@ -92,13 +92,13 @@ __device__ __forceinline__ void dft16(float2* v) {
 //   X_k = v_0 + sum_{m=1..(R-1)/2} [ (v_m + v_{R-m}) cos(2 pi k m / R) + j (v_m - v_{R-m}) sin(2 pi k m / R) ]
 // and X_{R-k} is the same with the second term negated.  Indices are compile-time after unrolling, so
 // the cosines/sines fold into immediates.
-__host__ __device__ constexpr float cos_r(int R, int i) {   // cos(2 pi i / R), R in {5, 7}, 0 <= i < R
-  return R == 5 ? (i == 0 ? 1.0f : (i == 1 || i == 4) ? 0.30901699437494742410f : -0.80901699437494742410f)
+__host__ __device__ constexpr float cos_r(int R, int i) {   // cos(2 pi i / R), R in {3, 5, 7}, 0 <= i < R
+  return R == 3 ? (i == 0 ? 1.0f : -0.5f) : R == 5 ? (i == 0 ? 1.0f : (i == 1 || i == 4) ? 0.30901699437494742410f : -0.80901699437494742410f)
                 : (i == 0 ? 1.0f : (i == 1 || i == 6) ? 0.62348980185873353053f
                    : (i == 2 || i == 5) ? -0.22252093395631440429f : -0.90096886790241912624f);
 }
 __host__ __device__ constexpr float sin_r(int R, int i) {   // sin(2 pi i / R)
-  return R == 5 ? (i == 0 ? 0.0f : i == 1 ? 0.95105651629515357212f : i == 2 ? 0.58778525229247312917f
+  return R == 3 ? (i == 0 ? 0.0f : i == 1 ? 0.86602540378443864676f : -0.86602540378443864676f) : R == 5 ? (i == 0 ? 0.0f : i == 1 ? 0.95105651629515357212f : i == 2 ? 0.58778525229247312917f
                    : i == 3 ? -0.58778525229247312917f : -0.95105651629515357212f)
                 : (i == 0 ? 0.0f : i == 1 ? 0.78183148246802980871f : i == 2 ? 0.97492791218182360702f
                    : i == 3 ? 0.43388373911755812048f : i == 4 ? -0.43388373911755812048f
@@ -130,6 +130,7 @@ template <int R> __device__ __forceinline__ void dft_odd(float2* v) {
   for (int i = 0; i < R; i++) v[i] = out[i];
 }
 template <int R> __device__ __forceinline__ void dft(float2* v);
+template <> __device__ __forceinline__ void dft<3>(float2* v) { dft_odd<3>(v); }
 template <> __device__ __forceinline__ void dft<5>(float2* v) { dft_odd<5>(v); }
 template <> __device__ __forceinline__ void dft<7>(float2* v) { dft_odd<7>(v); }
 template <> __device__ __forceinline__ void dft<2>(float2* v) { dft2(v[0], v[1]); }

@@ -45,7 +45,9 @@ struct chz {
   int device = 0;
   int sm_count = 148;
   uint32_t M = 0, P = 0, L = 0, os = 1, D = 0;
-  bool generic = false;                 // M is not a power of two >= 8: direct FIR + O(M^2) DFT kernels
+  bool generic = false;                 // no compile-time radix plan for M (see mixed_np)
+  int mixed_np = 0, mixed_r[12] = {0};  // generic M with prime factors <= 7: run-time mixed-radix plan; 0 = O(M^2) DFT
+  int fir_bpb = 0;                      // register-window FIR block size for run-time M (0 = direct FIR kernel)
   std::vector<float> taps;              // prototype as given (unscaled), h[qM + p]
   float* d_taps[17] = {nullptr};        // per bit width: taps * 2^-(bw-1), uploaded on first use
   float2* d_tw = nullptr;               // e^{+j 2 pi i / M}

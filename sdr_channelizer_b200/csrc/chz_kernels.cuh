@@ -24,6 +24,7 @@ struct ChanParams {
   long long row_base;    // first stream row produced by this call
   long long nrows;       // rows produced by this call
   int M, D, os;          // os = M / D (1 or 2)
+  int bpb;               // k_fir with run-time M: branches per 128-thread block (a divisor of M, <= 128)
   int span_rows;         // rows of one phase handled between window warm-ups (multiple of P)
   long long spans_per_phase;
 };
@@ -183,7 +184,9 @@ __device__ __forceinline__ void fir_span(const ChanParams& prm, const Span& sp, 
 template <int P, bool IN16, int MT>
 __global__ void __launch_bounds__(128, 4) k_fir(ChanParams prm, float2* __restrict__ u) {
   const int Mv = MT ? MT : prm.M;
-  const int bpb = Mv < 128 ? Mv : (Mv % 128 == 0 ? 128 : 112);   // branches per block (560 = 5 x 112)
+  // branches per block: 128, or for channel counts that are not multiples of 128 the largest divisor of M
+  // the host found (560 = 5 x 112, 200 = 2 x 100, ...)
+  const int bpb = MT ? (MT < 128 ? MT : 128) : prm.bpb;
   const int nbb = Mv / bpb;                        // branch blocks
   const int groups = 128 / bpb;                    // spans handled side by side in one block
   const int bb = blockIdx.x % nbb, g = threadIdx.x / bpb;
@@ -247,6 +250,81 @@ static __global__ void __launch_bounds__(256) k_dft_rows_any(const float2* u, fl
         if (idx >= M) idx -= M;
       }
       y[r * M + k] = acc;
+    }
+  }
+}
+
+// ---- any 7-smooth M: run-time mixed-radix Stockham row FFT ------------------------------------------
+// Channel counts follow the radio's sample rate (M = fs*1e-6, matlab/create_pdws_channelized.m:31): 40,
+// 48, 80, 100, 112, 120, 200 ... are as natural as 56.  Only 56 and 560 have compile-time plans; every
+// other M whose prime factors are 2, 3, 5, 7 runs this kernel: radices from {16, 8, 4, 2, 3, 5, 7} chosen on
+// the host (MixedPlan), one Stockham pass per radix in shared memory (unpadded), twiddles from the same
+// per-pass table layout as the compiled plans.  M with a larger prime factor keeps the O(M^2) DFT below.
+struct MixedPlan { int np; int r[12]; };
+
+template <int R>
+__device__ __forceinline__ void mixed_pass(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ tw,
+                                           int M, int NS, int rows, int t, int NT, float2* __restrict__ gout, int vrows) {
+  const int BPR = M / R, total = rows * BPR;
+  for (int b = t; b < total; b += NT) {
+    const int row = b / BPR, j = b - row * BPR;
+    const float2* s = src + row * M;
+    float2 v[R];
+    #pragma unroll
+    for (int q = 0; q < R; q++) v[q] = s[j + q * BPR];
+    const int k = j % NS;
+    if (NS > 1) {
+      #pragma unroll
+      for (int q = 1; q < R; q++) v[q] = cmul(v[q], tw[(q - 1) * NS + k]);     // W_{NS R}^{q k}
+    }
+    dft<R>(v);
+    const int j0 = (j - k) * R + k;
+    if (gout) {
+      if (row < vrows) {
+        float2* g = gout + (long long)row * M;
+        #pragma unroll
+        for (int q = 0; q < R; q++) g[j0 + q * NS] = v[q];
+      }
+    } else {
+      float2* d = dst + row * M;
+      #pragma unroll
+      for (int q = 0; q < R; q++) d[j0 + q * NS] = v[q];
+    }
+  }
+}
+
+// One block transforms `rows_per_block` rows at a time.  Dynamic smem: 2 * rows_per_block * M float2.
+static __global__ void __launch_bounds__(256) k_fft_rows_mixed(const float2* u, float2* y, const float2* __restrict__ tw_g, int M,
+                                                               long long nrows, int rows_per_block, MixedPlan plan) {
+  extern __shared__ float2 smem[];
+  float2* buf0 = smem;
+  float2* buf1 = smem + (size_t)rows_per_block * M;
+  const int t = threadIdx.x;
+  for (long long r0 = (long long)blockIdx.x * rows_per_block; r0 < nrows; r0 += (long long)gridDim.x * rows_per_block) {
+    const int vrows = (int)((nrows - r0) < rows_per_block ? (nrows - r0) : rows_per_block);
+    __syncthreads();
+    for (int e = t; e < vrows * M; e += 256) buf0[e] = u[r0 * M + e];
+    __syncthreads();
+    float2* src = buf0;
+    float2* dst = buf1;
+    int NS = 1, off = 0;
+    for (int pass = 0; pass < plan.np; pass++) {
+      const int R = plan.r[pass];
+      float2* gout = pass == plan.np - 1 ? y + r0 * M : nullptr;
+      const float2* tw = tw_g + off;
+      switch (R) {
+        case 16: mixed_pass<16>(src, dst, tw, M, NS, vrows, t, 256, gout, vrows); break;
+        case 8: mixed_pass<8>(src, dst, tw, M, NS, vrows, t, 256, gout, vrows); break;
+        case 7: mixed_pass<7>(src, dst, tw, M, NS, vrows, t, 256, gout, vrows); break;
+        case 5: mixed_pass<5>(src, dst, tw, M, NS, vrows, t, 256, gout, vrows); break;
+        case 4: mixed_pass<4>(src, dst, tw, M, NS, vrows, t, 256, gout, vrows); break;
+        case 3: mixed_pass<3>(src, dst, tw, M, NS, vrows, t, 256, gout, vrows); break;
+        default: mixed_pass<2>(src, dst, tw, M, NS, vrows, t, 256, gout, vrows); break;
+      }
+      if (NS > 1) off += (R - 1) * NS;                   // the first pass has no twiddles and no table entries
+      NS *= R;
+      float2* sw = src; src = dst; dst = sw;
+      __syncthreads();
     }
   }
 }

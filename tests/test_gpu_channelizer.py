@@ -47,7 +47,9 @@ def test_unpack_bit_exact_all_values(orc, bw):
 
 
 # ---- K3 against cuFFT ----------------------------------------------------------------------------------
-@pytest.mark.parametrize("M", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 56, 560])   # 56 = 8*7, 560 = 16*5*7: radix-7/5 passes
+@pytest.mark.parametrize("M", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 56, 560,   # 56 = 8*7, 560 = 16*5*7: radix-7/5 passes
+                               2, 6, 7, 12, 40, 48, 100, 112, 120, 200, 243, 768, 1000, 3000, 3584,   # run-time mixed-radix plans
+                               22, 61])                                                         # O(M^2) DFT (prime factor > 7)
 def test_fft_stage_matches_cufft(M):
     torch = _torch()
     rows = 37 if M >= 1024 else 333
@@ -274,11 +276,15 @@ def test_edge_lengths_ragged_and_tiny(orc, M, P, os_, bw):
 
 
 @pytest.mark.parametrize("M,P,os_,kind", [(56, 12, 1, "q11"), (56, 12, 2, "full"), (12, 8, 1, "i8"), (7, 5, 1, "full"),
-                                         (100, 16, 2, "full"), (560, 12, 1, "q11"), (4, 8, 1, "i8"), (2, 3, 2, "full")])
+                                         (100, 16, 2, "full"), (560, 12, 1, "q11"), (4, 8, 1, "i8"), (2, 3, 2, "full"),
+                                         (40, 12, 1, "q11"), (48, 16, 2, "full"), (80, 12, 1, "i8"), (120, 8, 1, "q11"), (200, 12, 2, "full"),
+                                         (768, 12, 1, "q11"), (1000, 12, 1, "full"), (61, 12, 1, "q11"), (22, 12, 2, "full"), (250, 5, 1, "q11")])
 def test_non_power_of_two_channel_counts(orc, M, P, os_, kind):
     """The reference's own M is fs*1e-6 (56 for the b200mini at 56 MS/s, create_pdws_channelized.m:31);
-    56 and 560 have radix-7/5 plans and run the fused kernel, every other such size runs the functional
-    any-M path.  Same tolerance, and streaming stays bit-identical."""
+    56 and 560 have compile-time radix-7/5 plans and run the fused kernel; other channel counts with prime
+    factors <= 7 (40, 48, 100, 200 ... as natural as 56 for other sample rates) run the register-window FIR +
+    a run-time mixed-radix row FFT; the rest (61, 22) the direct FIR / O(M^2) DFT.  Same tolerance, and
+    streaming stays bit-identical."""
     _torch()
     n = M * 300 + 5
     iq, bw = _gen(kind, n, M, seed=M)

@@ -4,7 +4,7 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import sdr_channelizer_b200 as pkg
-for M, P, bw in ((56, 12, 16), (560, 12, 16), (61, 12, 12), (64, 12, 12)):
+for M, P, bw in ((56, 12, 16), (560, 12, 16), (61, 12, 12), (64, 12, 12), (40, 12, 16), (100, 12, 16), (200, 12, 16), (768, 12, 16)):
     n = 560_000_000 // M * M if M != 61 else 56_000_000 // M * M     # 10 s at 56 MS/s
     x = torch.randint(-2000, 2000, (n, 2), dtype=torch.int16, device="cuda")
     rows = n // M
