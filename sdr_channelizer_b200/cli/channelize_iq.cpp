@@ -1,55 +1,75 @@
 // channelize_iq — command-line companion of the reference's record tools: takes a recording written
 // by blade_record_iq_* / usrp_record_iq_* (cpp/IqPacket.h header + interleaved I/Q), channelizes it on
-// the GPU through libchannelizer and writes the channel matrix and the PDW table.
+// the GPU through libchannelizer and writes the channel matrix and the PDW table.  Given a DIRECTORY it
+// watches it and processes every dwell file the recorders drop there (one file per dwell,
+// cpp/blade_record_iq_12bit.cpp:316-324), in name order -- the recorder's file names are UTC time stamps
+// (cpp/Helper.cpp:6-23), so name order is time order.
 // Style follows the reference tools: positional arguments, a usage text, `return __LINE__` on failure
 // (cpp/blade_record_iq_12bit.cpp:31-37,54-59).
+#include <dirent.h>
+#include <sys/stat.h>
+
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "channelizer.h"
 
 #define CHECK(call)                                                                              \
   do {                                                                                           \
-    const int status = (call);                                                                   \
-    if (status != 0) {                                                                           \
-      std::cerr << #call << " failed: " << chz_strerror(status) << " " << chz_last_cuda_error()  \
+    const int status_ = (call);                                                                  \
+    if (status_ != 0) {                                                                          \
+      std::cerr << #call << " failed: " << chz_strerror(status_) << " " << chz_last_cuda_error() \
                 << std::endl;                                                                    \
       return __LINE__;                                                                           \
     }                                                                                            \
   } while (0)
 
-int main(int argc, char** argv) {
-  if (argc < 5) {
-    std::cerr << "Usage: " << argv[0]
-              << " <recording.iq> <channels (0 = sampleRate*1e-6)> <tapsPerBand> <oversample 1|2>"
-                 " [snrThresholdDb=15] [outputPrefix]"
-              << std::endl;
-    return __LINE__;
-  }
-  const char* path = argv[1];
-  uint32_t channels = (uint32_t)std::atoi(argv[2]);
-  const uint32_t tapsPerBand = (uint32_t)std::atoi(argv[3]);
-  const uint32_t oversample = (uint32_t)std::atoi(argv[4]);
-  const double snrThresholdDb = argc > 5 ? std::atof(argv[5]) : 15.0;
-  const std::string prefix = argc > 6 ? argv[6] : "";
+namespace {
 
+struct Options {
+  uint32_t channels = 0, tapsPerBand = 12, oversample = 1;
+  double snrThresholdDb = 15.0;
+};
+
+// One channelizer handle is kept across files while the geometry stays the same (chz_reset = a fresh
+// dsp.Channelizer per file, matlab/create_pdws_channelized.m:33).
+struct Engine {
+  chz_t* chan = nullptr;
+  uint32_t channels = 0;
+  ~Engine() { if (chan) chz_destroy(chan); }
+};
+
+// 0 = done, > 0 = failure line, -1 = the file is not complete yet (watch mode retries it)
+int processOne(Engine& eng, const Options& opt, const std::string& path, const std::string& prefix) {
   chz_iq_t* file = nullptr;
   chz_iq_info_t info;
-  CHECK(chz_open_iq(path, &file, &info));
-  std::cout << "File format " << info.format << ", " << info.num_samples << " samples, " << info.bit_width
+  const int rc = chz_open_iq(path.c_str(), &file, &info);
+  if (rc == CHZ_ESIZE || rc == CHZ_EIO) return -1;     // header or payload still being written
+  CHECK(rc);
+  std::cout << path << ": file format " << info.format << ", " << info.num_samples << " samples, " << info.bit_width
             << " bits, fs " << info.fs_sps << " sps, fc " << info.fc_hz << " Hz, board '" << info.board_name << "'"
             << std::endl;
+  uint32_t channels = opt.channels;
   if (channels == 0) channels = (uint32_t)(info.fs_sps * 1e-6 + 0.5);   // create_pdws_channelized.m:31
-
-  std::vector<float> taps((size_t)channels * tapsPerBand);
-  CHECK(chz_design_prototype(channels, tapsPerBand, 80.0, taps.data()));
-  chz_t* chan = nullptr;
-  CHECK(chz_create(channels, taps.data(), (uint32_t)taps.size(), oversample, &chan));
+  if (!eng.chan || eng.channels != channels) {
+    if (eng.chan) chz_destroy(eng.chan);
+    eng.chan = nullptr;
+    std::vector<float> taps((size_t)channels * opt.tapsPerBand);
+    CHECK(chz_design_prototype(channels, opt.tapsPerBand, 80.0, taps.data()));
+    CHECK(chz_create(channels, taps.data(), (uint32_t)taps.size(), opt.oversample, &eng.chan));
+    eng.channels = channels;
+  } else {
+    CHECK(chz_reset(eng.chan));
+  }
+  chz_t* chan = eng.chan;
 
   const uint64_t rows = chz_rows_for(chan, info.num_samples);
   chz_cf32* out = nullptr;
@@ -64,14 +84,14 @@ int main(int argc, char** argv) {
 
   chz_pdw_params_t prm;
   std::memset(&prm, 0, sizeof prm);
-  prm.snr_threshold_db = snrThresholdDb;
+  prm.snr_threshold_db = opt.snrThresholdDb;
   prm.sat_level = 0.9999;
   prm.fc_hz = (double)info.fc_hz;
   prm.fs_sps = (double)info.fs_sps;
   prm.t0 = info.sample_start_time;
   prm.use_trailing_threshold = 0;
   uint64_t npdw = 0;
-  int status = chz_pdws(chan, &prm, nullptr, 0, &npdw);
+  const int status = chz_pdws(chan, &prm, nullptr, 0, &npdw);
   if (status != 0 && status != CHZ_ECAPACITY) CHECK(status);
   std::vector<chz_pdw_t> pdws(npdw);
   if (npdw) CHECK(chz_pdws_fetch(chan, pdws.data(), npdw, &npdw));
@@ -89,18 +109,92 @@ int main(int argc, char** argv) {
     if (!fc) return __LINE__;
     std::fwrite(out, sizeof(chz_cf32), got * channels, fc);
     std::fclose(fc);
-    const std::string pdwName = prefix + ".pdw.csv";
-    FILE* fp = std::fopen(pdwName.c_str(), "w");
+    // the table is written under a temporary name and renamed, so a consumer never sees half of it
+    const std::string pdwName = prefix + ".pdw.csv", tmpName = pdwName + ".part";
+    FILE* fp = std::fopen(tmpName.c_str(), "w");
     if (!fp) return __LINE__;
     std::fprintf(fp, "toa_s,freq_hz,pw_s,snr_db,sat,amp,channel\n");
     for (const chz_pdw_t& p : pdws)
       std::fprintf(fp, "%.9f,%.3f,%.9g,%.4f,%u,%.6g,%u\n", p.toa_s, p.freq_hz, p.pw_s, p.snr_db, p.saturated, p.amp,
                    p.channel);
     std::fclose(fp);
+    if (std::rename(tmpName.c_str(), pdwName.c_str()) != 0) return __LINE__;
     std::cout << "Wrote " << chanName << " and " << pdwName << std::endl;
   }
   if (out) chz_free_host(out);
-  chz_destroy(chan);
   chz_close_iq(file);
+  return 0;
+}
+
+bool isDirectory(const std::string& p) {
+  struct stat st;
+  return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+
+bool exists(const std::string& p) {
+  struct stat st;
+  return stat(p.c_str(), &st) == 0;
+}
+
+std::vector<std::string> listIq(const std::string& dir) {
+  std::vector<std::string> names;
+  if (DIR* d = opendir(dir.c_str())) {
+    while (const dirent* e = readdir(d)) {
+      const std::string n = e->d_name;
+      if (n.size() > 3 && n.compare(n.size() - 3, 3, ".iq") == 0) names.push_back(n);
+    }
+    closedir(d);
+  }
+  std::sort(names.begin(), names.end());
+  return names;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 5) {
+    std::cerr << "Usage: " << argv[0]
+              << " <recording.iq | directory to watch> <channels (0 = sampleRate*1e-6)> <tapsPerBand> <oversample 1|2>"
+                 " [snrThresholdDb=15] [outputPrefix | output directory] [idleSec=10 (watch mode: exit after this"
+                 " long without a new file, or when a file named 'stop' appears)]"
+              << std::endl;
+    return __LINE__;
+  }
+  const std::string input = argv[1];
+  Options opt;
+  opt.channels = (uint32_t)std::atoi(argv[2]);
+  opt.tapsPerBand = (uint32_t)std::atoi(argv[3]);
+  opt.oversample = (uint32_t)std::atoi(argv[4]);
+  opt.snrThresholdDb = argc > 5 ? std::atof(argv[5]) : 15.0;
+  const std::string prefix = argc > 6 ? argv[6] : "";
+  const double idleSec = argc > 7 ? std::atof(argv[7]) : 10.0;
+  Engine eng;
+
+  if (!isDirectory(input)) return processOne(eng, opt, input, prefix);
+
+  // watch mode: dwell files appear one by one while the recorder runs
+  const std::string outDir = prefix.empty() ? input : prefix;
+  std::set<std::string> done;
+  auto lastWork = std::chrono::steady_clock::now();
+  uint64_t processed = 0;
+  for (;;) {
+    bool worked = false;
+    for (const std::string& name : listIq(input)) {
+      if (done.count(name)) continue;
+      const std::string stem = name.substr(0, name.size() - 3);
+      const int rc = processOne(eng, opt, input + "/" + name, outDir + "/" + stem);
+      if (rc == -1) break;                       // still being written: files are handled in time order, so wait for it
+      if (rc != 0) return rc;
+      done.insert(name);
+      processed++;
+      worked = true;
+    }
+    const auto now = std::chrono::steady_clock::now();
+    if (worked) lastWork = now;
+    if (exists(input + "/stop")) break;
+    if (std::chrono::duration<double>(now - lastWork).count() > idleSec) break;
+    if (!worked) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+  }
+  std::cout << "Processed " << processed << " recordings from " << input << std::endl;
   return 0;
 }

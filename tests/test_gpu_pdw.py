@@ -305,3 +305,71 @@ def test_predict_event_script_against_oracle(orc, tmp_path):
         assert abs(ev - (t0 - starts[0] + tp)) < 2e-3                     # the vertex sits where the emitter peaked
     assert abs(res["next_event"][0] - (res["event"][0] + 4.61962892466417)) < 1e-12
     assert abs(res["next_event"][-1] - orc.next_event_time(oevents)) < 1e-6
+
+
+# ---- channelize_iq CLI: one recording, and the directory-watch mode ------------------
+def _cli():
+    import os
+    p = os.path.join(os.path.dirname(pkg.LIB_PATH), "cli", "channelize_iq.out")
+    assert os.path.exists(p), "build the CLI with __graft_entry__.build()"
+    return p
+
+
+def _expected(path, M, P):
+    rec = pkg.read_iq(path)
+    ch = pkg.Channelizer(M, taps=pkg.design_prototype(M, P))
+    y = ch(rec.iq, rec.bitWidth).copy()
+    recs, _ = ch.pdws(rec.fs, rec.fc, rec.sampleStartTime)
+    ch.close()
+    return y, recs
+
+
+def test_cli_single_recording_and_watch_mode(tmp_path):
+    import os, subprocess, time
+    _torch()
+    M, P = 64, 12
+    files = []
+    for i in range(3):
+        iq, bw, fs = synth.pulsed_int16(M * 4000, M=M, seed=300 + i)
+        files.append((f"2024_01_0{i + 1}_00_00_00_000.iq", iq, bw, fs))     # Helper.cpp-style names: name order = time order
+    # one recording
+    one = str(tmp_path / files[0][0])
+    pkg.write_iq(one, files[0][1], fs=files[0][3], fc=2.4e9, bitWidth=files[0][2], sampleStartTime=50.0)
+    out = subprocess.run([_cli(), one, "0", str(P), "1", "15", str(tmp_path / "single")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    y, recs = _expected(one, M, P)                                          # channels = 0 -> fs*1e-6 = 64 (:31)
+    got = np.fromfile(str(tmp_path / "single.cf32"), dtype=np.complex64).reshape(-1, M)
+    assert np.array_equal(got.view(np.float32), y.view(np.float32))
+    rows = open(str(tmp_path / "single.pdw.csv")).read().strip().splitlines()
+    assert rows[0] == "toa_s,freq_hz,pw_s,snr_db,sat,amp,channel" and len(rows) - 1 == len(recs) > 0
+    # watch mode: files dropped into the directory while the tool runs, the last one in two pieces
+    watch, outd = tmp_path / "dwell", tmp_path / "out"
+    watch.mkdir(); outd.mkdir()
+    proc = subprocess.Popen([_cli(), str(watch), str(M), str(P), "1", "15", str(outd), "60"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        for name, iq, bw, fs in files[:2]:
+            pkg.write_iq(str(watch / name), iq, fs=fs, fc=2.4e9, bitWidth=bw, sampleStartTime=50.0)
+        name, iq, bw, fs = files[2]
+        whole = str(tmp_path / "whole.iq")
+        pkg.write_iq(whole, iq, fs=fs, fc=2.4e9, bitWidth=bw, sampleStartTime=50.0)
+        data = open(whole, "rb").read()
+        with open(str(watch / name), "wb") as f:                            # a recorder in the middle of its write
+            f.write(data[:len(data) // 3]); f.flush()
+            time.sleep(0.5)
+            assert not (outd / (name[:-3] + ".pdw.csv")).exists()
+            f.write(data[len(data) // 3:])
+        deadline = time.time() + 120
+        while time.time() < deadline and not all((outd / (n[:-3] + ".pdw.csv")).exists() for n, *_ in files):
+            time.sleep(0.1)
+        (watch / "stop").write_text("")
+        so, se = proc.communicate(timeout=120)
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+    assert proc.returncode == 0, se
+    assert "Processed 3 recordings" in so
+    for name, *_ in files:
+        y, recs = _expected(str(watch / name), M, P)
+        got = np.fromfile(str(outd / (name[:-3] + ".cf32")), dtype=np.complex64).reshape(-1, M)
+        assert np.array_equal(got.view(np.float32), y.view(np.float32))
+        assert len(open(str(outd / (name[:-3] + ".pdw.csv"))).read().strip().splitlines()) - 1 == len(recs)
