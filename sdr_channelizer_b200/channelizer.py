@@ -366,5 +366,43 @@ def predict_event(recordings, SNR_THRESHOLD=20.0, min_peak=0.9):
     return {k: np.asarray(v) for k, v in out.items()}
 
 
+def stft(iq, bitWidth, fs, Window=None):
+    """[s, f, t] = stft(iq, fs, 'Window', hamming(768), 'OverlapLength', 0) of matlab/spectrogram_my_iq.m:114 on
+    the GPU.  A short-time Fourier transform without overlap IS a critically sampled filterbank with one tap
+    per band: M = numel(Window) channels, prototype = the (time-reversed) window.  Segment m of the signal is
+    row m+1 of the channelizer fed with one leading zero sample, up to the fixed phase factor
+    e^{-j 2 pi k (M-1)/M} (the filterbank counts taps back from a row's newest sample and uses the e^{+j}
+    kernel) which is applied here.  FFTLength is taken equal to the window length (the script leaves it at
+    the toolbox default; the toolbox source is not available: unpinned).  Two-sided, centred frequency axis.
+    -> (s complex64 [M, segments], f [M] Hz, t [segments] s)."""
+    w = np.hamming(768) if Window is None else np.asarray(Window, dtype=np.float64)     # hamming(768): symmetric
+    M = int(w.size)
+    iq = np.ascontiguousarray(iq).reshape(-1, 2)
+    nseg = iq.shape[0] // M
+    ch = Channelizer(M, taps=np.ascontiguousarray(w[::-1], dtype=np.float32))
+    try:
+        x = np.zeros((1 + nseg * M + (M - 1), 2), dtype=iq.dtype)                       # one zero in front, M-1 behind
+        x[1:1 + nseg * M] = iq[:nseg * M]
+        y = ch(x, bitWidth)[1:1 + nseg]
+    finally:
+        ch.close()
+    k = np.arange(M)
+    s_nat = y * np.exp(-2j * np.pi * k * (M - 1) / M).astype(np.complex64)
+    s = np.fft.fftshift(s_nat, axes=1).T                                               # 'centered' (the default range)
+    f = (np.arange(M) - M // 2) * (fs / M)
+    t = (np.arange(nseg) * M + M / 2) / fs
+    return s, f, t
+
+
+def spectrogram_my_iq(rec):
+    """The math of matlab/spectrogram_my_iq.m:104-115 for one recording (path or IqRecording): normalise, STFT
+    with a 768-point Hamming window and no overlap, power abs(s).^2 over (f + fc, t).  Plotting is the caller's.
+    -> dict(power [768, segments], f_hz (absolute), t_s)."""
+    if not isinstance(rec, IqRecording):
+        rec = read_iq(rec)
+    s, f, t = stft(rec.iq, rec.bitWidth, rec.fs)
+    return {"power": np.abs(s) ** 2, "f_hz": f + rec.fc, "t_s": t}
+
+
 __all__ = ["IqRecording", "read_iq", "write_iq", "design_prototype", "Channelizer", "unpack_ptr",
-           "create_pdws_channelized", "create_pdws", "predict_event", "event_peak_time", "next_event_time", "ChannelizerError"]
+           "create_pdws_channelized", "create_pdws", "predict_event", "event_peak_time", "next_event_time", "stft", "spectrogram_my_iq", "ChannelizerError"]

@@ -361,3 +361,24 @@ def test_large_run_spot_rows_and_linearity(orc, M, P, os_, bw, nframes):
         got = outs[0][m].cpu().numpy()
         assert synth.rel_rms(got, ref) <= TOL, m
     ch.close()
+
+
+def test_stft_of_spectrogram_script(orc, tmp_path):
+    """matlab/spectrogram_my_iq.m:104-115: 768-point Hamming STFT without overlap == the M = 768, one-tap-per-band
+    filterbank (run-time mixed-radix plan 16*16*3) up to a fixed phase factor; against numpy's FFT of the
+    windowed segments of the oracle's normalised samples."""
+    _torch()
+    fs, n = 56e6, 768 * 300 + 401
+    iq, bw = synth.tones_int16_q11(n, 64, seed=17)
+    s, f, t = pkg.stft(iq, bw, fs)
+    x = orc.unpack(iq, bw)
+    nseg = n // 768
+    ref = np.fft.fftshift(np.fft.fft(x[:nseg * 768].reshape(nseg, 768) * np.hamming(768), axis=1), axes=1).T
+    assert s.shape == ref.shape == (768, nseg)
+    assert synth.rel_rms(s, ref) <= TOL
+    assert np.allclose(f, (np.arange(768) - 384) * fs / 768) and np.allclose(t, (np.arange(nseg) * 768 + 384) / fs)
+    path = str(tmp_path / "spec.iq")
+    pkg.write_iq(path, iq, fs=fs, fc=1.0e9, bitWidth=bw)
+    sp = pkg.spectrogram_my_iq(path)
+    assert sp["power"].shape == (768, nseg) and np.allclose(sp["power"], np.abs(ref) ** 2, rtol=1e-4, atol=1e-9 * np.max(np.abs(ref)) ** 2)
+    assert sp["f_hz"][384] == 1.0e9
