@@ -373,3 +373,25 @@ def test_cli_single_recording_and_watch_mode(tmp_path):
         got = np.fromfile(str(outd / (name[:-3] + ".cf32")), dtype=np.complex64).reshape(-1, M)
         assert np.array_equal(got.view(np.float32), y.view(np.float32))
         assert len(open(str(outd / (name[:-3] + ".pdw.csv"))).read().strip().splitlines()) - 1 == len(recs)
+
+
+def test_sharded_pdws_hysteresis_across_boundaries():
+    """Wideband extractor (create_pdws.m: 18 dB up, 3 dB down) on shards: after a leading edge the samples that
+    sit BETWEEN the two thresholds keep the pulse alive, so a shard made only of such samples hands its entry
+    state on unchanged (exit code 2) and the FSM state has to be folded over several shards."""
+    M, rows = 1, 4000
+    rng = np.random.default_rng(11)
+    y = (rng.normal(0, 0.001, rows) + 1j * rng.normal(0, 0.001, rows)).astype(np.complex64).reshape(-1, 1)
+    def pulse(a, top, tail):                  # `top` strong rows, then a long plateau between the thresholds
+        y[a:a + top, 0] += 0.5
+        y[a + top:a + top + tail, 0] += 0.01  # ~ 8x the noise floor: above 3 dB, below 18 dB
+    pulse(300, 40, 900)                       # plateau spans rows 340..1240
+    pulse(2000, 10, 30)
+    pulse(3100, 200, 500)
+    kw = dict(SNR_THRESHOLD=18.0, TRAILING_EDGE_THRESHOLD=3.0)
+    whole, nf = _pdws_on_matrix(y, 1e6, **kw)
+    assert [(int(r.toa_row), int(r.end_row)) for r in whole][0][0] == 301 and whole[0].end_row > 1200 and len(whole) == 3
+    for bounds in ([0, 500, 800, 1100, 4000], [0, 339, 340, 341, 2005, 4000], [0, 3150, 3400, 4000]):
+        for recs, nfs in _sharded_on_one_gpu(y, bounds, 1e6, **kw):
+            _same_records(recs, whole)
+            assert np.array_equal(nfs, nf)
