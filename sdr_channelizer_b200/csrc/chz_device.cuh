@@ -256,12 +256,18 @@ __device__ __forceinline__ void fft_tile_to_global(float2* buf0, float2* buf1, c
     stockham_pass<M, PL::r0, 1, ROWS, NT, false, false>(buf0, buf1, tw, twr, t, gout, grow_stride, vlo, vhi);
     sync();
     constexpr int S = RowStride<M>::value;
-    #pragma unroll
-    for (int e0 = 0; e0 < ROWS * M; e0 += NT) {
-      const int e = e0 + t;
-      if ((ROWS * M) % NT != 0 && e >= ROWS * M) break;
-      const int row = e / M, i = e % M;
-      if (row >= vlo && row < vhi) gout[(long long)row * grow_stride + i] = buf1[row * S + padi<M>(i)];
+    if constexpr (NT == M) {   // fused kernel: thread t owns channel t of every row of the tile
+      #pragma unroll
+      for (int row = 0; row < ROWS; row++)
+        if (row >= vlo && row < vhi) gout[(long long)row * grow_stride + t] = buf1[row * S + padi<M>(t)];
+    } else {
+      #pragma unroll
+      for (int e0 = 0; e0 < ROWS * M; e0 += NT) {
+        const int e = e0 + t;
+        if ((ROWS * M) % NT != 0 && e >= ROWS * M) break;
+        const int row = e / M, i = e % M;
+        if (row >= vlo && row < vhi) gout[(long long)row * grow_stride + i] = buf1[row * S + padi<M>(i)];
+      }
     }
   } else if constexpr (PL::np == 2) {
     stockham_pass<M, PL::r0, 1, ROWS, NT, false, false>(buf0, buf1, tw, twr, t, gout, grow_stride, vlo, vhi);

@@ -413,7 +413,11 @@ template <int M, int P> struct FusedCfg {
   // rows per FFT tile: largest divisor of P keeping the two tile buffers of a block under ~72 KB
   static constexpr int RTMAX = (72 * 1024) / (2 * 8 * RowStride<M>::value * G);
   static constexpr int RT = RTMAX >= P ? P : (P % 8 == 0 && RTMAX >= 8 ? 8 : (P % 6 == 0 && RTMAX >= 6 ? 6 : (P % 4 == 0 && RTMAX >= 4 ? 4 : (P % 2 == 0 && RTMAX >= 2 ? 2 : 1))));
-  static constexpr size_t SMEM = (size_t)(M + G * 2 * RT * RowStride<M>::value) * sizeof(float2);
+  // float2 per group (two tile buffers).  M = 8: four groups share a warp and two a half-warp (the unit a
+  // 64-bit shared access is processed in); 8 elements of padding put neighbouring groups 16 banks apart
+  // (measured without it: half of all shared wavefronts were bank conflicts, LSU data pipe 98 % busy).
+  static constexpr int GSTRIDE = 2 * RT * RowStride<M>::value + (M == 8 ? 8 : 0);
+  static constexpr size_t SMEM = (size_t)(M + G * GSTRIDE) * sizeof(float2);
 };
 
 template <int M> __device__ __forceinline__ void group_sync(int g) {
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 
   // flow, so they meet every barrier) without storing, and take their share of the FFT butterflies
   const bool branch = MG == M || t < M;
   const int p = branch ? t : M - 1;
-  float2* buf0 = smem + M + (size_t)g * 2 * RT * S;   // [RT][S]
+  float2* buf0 = smem + M + (size_t)g * CF::GSTRIDE;   // [RT][S]
   float2* buf1 = buf0 + RT * S;
   for (int i = threadIdx.x; i < M; i += NT) tw[i] = prm.tw[i];
   float2 twr[TwReg<M, MG>::count];
