@@ -410,8 +410,10 @@ template <int M, int P> struct FusedCfg {
   static constexpr int MG = GroupThreads<M>::value;  // threads per group (M rounded up to whole warps)
   static constexpr int NT = MG < 256 ? 256 / MG * MG : MG;   // threads per block
   static constexpr int G = NT / MG;                  // groups per block
-  // rows per FFT tile: largest divisor of P keeping the two tile buffers of a block under ~72 KB
-  static constexpr int RTMAX = (72 * 1024) / (2 * 8 * RowStride<M>::value * G);
+  // rows per FFT tile: largest divisor of P keeping the two tile buffers of a block under ~72 KB (several
+  // blocks per SM); blocks of >= 512 threads are alone on their SM anyway (registers) and take up to 200 KB:
+  // twice the rows per barrier round (M = 512: barrier stalls were 23 % of all samples with 8-row tiles)
+  static constexpr int RTMAX = ((NT >= 512 ? 200 : 72) * 1024) / (2 * 8 * RowStride<M>::value * G);
   static constexpr int RT = RTMAX >= P ? P : (P % 8 == 0 && RTMAX >= 8 ? 8 : (P % 6 == 0 && RTMAX >= 6 ? 6 : (P % 4 == 0 && RTMAX >= 4 ? 4 : (P % 2 == 0 && RTMAX >= 2 ? 2 : 1))));
   // float2 per group (two tile buffers).  M = 8: four groups share a warp and two a half-warp (the unit a
   // 64-bit shared access is processed in); 8 elements of padding put neighbouring groups 16 banks apart
