@@ -214,7 +214,8 @@ def _same_records(a, b):
         assert bytes(x) == bytes(z), ((x.toa_row, x.end_row, x.channel, x.amp, x.freq_hz), (z.toa_row, z.end_row, z.channel, z.amp, z.freq_hz))
 
 
-@pytest.mark.parametrize("bounds", [[0, 200, 400, 600], [0, 199, 600], [0, 1, 2, 600], [0, 64, 128, 192, 256, 320, 384, 600]])
+@pytest.mark.parametrize("bounds", [[0, 200, 400, 600], [0, 199, 600], [0, 1, 2, 600], [0, 64, 128, 192, 256, 320, 384, 600],
+                                    [0, 0, 300, 300, 600, 600]])      # ranks that hold no rows at all
 def test_sharded_pdws_identical_to_one_gpu(bounds):
     """Every boundary case (tests/test_sharding.py::_pdw_matrix): records and noise floor of the sharded
     extractor are byte-identical to chz_pdws_dev on the whole matrix, on every rank."""

@@ -135,7 +135,7 @@ def _pdw_worker(rank, world, port, y, bounds, out_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("bounds", [[0, 200, 400, 600], [0, 600], [0, 199, 600], [0, 1, 2, 600]])
+@pytest.mark.parametrize("bounds", [[0, 200, 400, 600], [0, 600], [0, 199, 600], [0, 1, 2, 600], [0, 0, 600, 600]])
 def test_sharded_pdws_gloo_equal_the_oracle_on_the_stitched_matrix(tmp_path, orc, bounds):
     """World-size 1..3 gloo runs of create_pdws_sharded (numpy stand-in for the GPU stages) against the
     oracle's create_pdws_channelized.m restatement on the whole matrix: same pulses, same order, same rows."""
