@@ -112,8 +112,6 @@ int chz_set_stream(chz_t* h, void* cuda_stream);
 #define CHZ_OPT_RETAIN        1  /* 1 (default): chz_process keeps its output rows on the device for chz_pdws */
 #define CHZ_OPT_CHUNK_ROWS    2  /* host path: rows per pipelined H2D/compute/D2H chunk (0 = auto) */
 #define CHZ_OPT_FORCE_PATH    3  /* 0 auto, 1 fused kernel, 2 split FIR + row-FFT kernels, 3 cluster kernel with an L2 ring (M >= 1024), 4 warp-specialised kernel (M = 64), 5 CTA-pair DSMEM kernel (M = 1024), 6 pipelined FIR+FFT task-queue kernel (M >= 1024), 7/8/9 L2-ring cluster kernel with 256-thread CTAs / + split arrive-wait pipelining / 512-thread pipelined, 10 DSMEM st.async cluster kernel; 3-10 are experiments measured slower than (or within 3 % of) the default, see DESIGN.md */
-#define CHZ_OPT_PDW_THREE_PASS 4  /* 1: always take the noise-floor median with three radix passes over y (default 0: inputs of
-                                  * >= 2^17 rows use one full pass + a sampled bracket, falling back when the bracket misses) */
 int chz_set_option(chz_t* h, int opt, int64_t value);
 
 uint32_t chz_num_channels(const chz_t* h);

@@ -534,7 +534,7 @@ void chz_destroy(chz_t* h) {
   h->cluster_ring.release();
   h->pipe_ctrl.release();
   for (int i = 0; i < 4; i++) { if (h->ev_fir[i]) cudaEventDestroy(h->ev_fir[i]); if (h->ev_fft[i]) cudaEventDestroy(h->ev_fft[i]); }
-  for (chzi::Scratch* sc : {&h->pdw_hist, &h->pdw_sel, &h->pdw_thr, &h->pdw_cnt, &h->pdw_ev, &h->pdw_pin, &h->pdw_pout, &h->pdw_code, &h->pdw_nf, &h->pdw_cand}) sc->release();
+  for (chzi::Scratch* sc : {&h->pdw_hist, &h->pdw_sel, &h->pdw_thr, &h->pdw_cnt, &h->pdw_ev, &h->pdw_pin, &h->pdw_pout, &h->pdw_code, &h->pdw_nf}) sc->release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -563,7 +563,6 @@ int chz_set_option(chz_t* h, int opt, int64_t value) {
   switch (opt) {
     case CHZ_OPT_RETAIN: h->retain = value != 0; return CHZ_OK;
     case CHZ_OPT_CHUNK_ROWS: if (value < 0) return CHZ_EINVAL; h->chunk_rows = value; return CHZ_OK;
-    case CHZ_OPT_PDW_THREE_PASS: h->pdw_three_pass = value != 0; return CHZ_OK;
     case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 10) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
     default: return CHZ_EINVAL;
   }

@@ -92,9 +92,7 @@ struct chz {
   uint64_t launches = 0;
 
   // PDW scratch (histograms, select state, thresholds, edge events, pulse lists)
-  chzi::Scratch pdw_hist, pdw_sel, pdw_thr, pdw_cnt, pdw_ev, pdw_pin, pdw_pout, pdw_code, pdw_nf, pdw_cand;
-  bool pdw_three_pass = false;          // CHZ_OPT_PDW_THREE_PASS
-  uint64_t median_fallbacks = 0;        // one-pass median attempts that had to fall back to the three radix passes
+  chzi::Scratch pdw_hist, pdw_sel, pdw_thr, pdw_cnt, pdw_ev, pdw_pin, pdw_pout, pdw_code, pdw_nf;
   uint64_t pdw_ev_cap = 1ull << 20;
 
   // PDW results of the last run

@@ -39,9 +39,8 @@ __device__ __forceinline__ uint32_t prefix_mask(int pass) { return pass == 0 ? 0
 // segments, i.e. whole DRAM sectors).
 // hist: [M][2][kBins] uint32.  Slot 0 is privatised in shared memory; slot 1 (only used when the two
 // order statistics have diverged into different buckets) goes straight to global atomics.
-// row_stride > 1: histogram of every row_stride-th row only (nrows = number of sampled rows).
 __global__ void __launch_bounds__(256) k_hist(const float2* __restrict__ y, long long nrows, int M, int pass,
-                                              const SelState* __restrict__ st, uint32_t* __restrict__ hist, long long row_stride) {
+                                              const SelState* __restrict__ st, uint32_t* __restrict__ hist) {
   __shared__ uint32_t sh[4 * kBins];
   for (int i = threadIdx.x; i < 4 * kBins; i += 256) sh[i] = 0;
   const int cl = threadIdx.x & 3, ch = blockIdx.x * 4 + cl;
@@ -64,7 +63,7 @@ __global__ void __launch_bounds__(256) k_hist(const float2* __restrict__ y, long
     #pragma unroll
     for (int u = 0; u < UN; u++) {
       const long long rr = r + 64LL * u;
-      v[u] = rr < r_end ? __ldg(y + rr * row_stride * M + ch) : make_float2(-1.f, 0.f);
+      v[u] = rr < r_end ? __ldg(y + rr * M + ch) : make_float2(-1.f, 0.f);
     }
     #pragma unroll
     for (int u = 0; u < UN; u++) {
@@ -118,89 +117,6 @@ __global__ void __launch_bounds__(256) k_select(uint32_t* __restrict__ hist, Sel
   __syncthreads();
   // clear both histogram rows of this channel for the next pass
   for (int i = threadIdx.x; i < 2 * kBins; i += 256) hist[(size_t)ch * 2 * kBins + i] = 0;
-}
-
-// ---- exact median in ONE full pass (large inputs) ---------------------------------------------------
-// The three radix passes read y three times.  For large inputs the median is first BRACKETED on a row
-// subsample (the same three passes over every 61st row, asking for the order statistics 4 sqrt(n_s) ranks
-// either side of the sample median: the true middle elements lie between them with overwhelming
-// probability); then one pass over all of y counts, per channel, the values below the bracket and copies
-// the few per cent inside it to a candidate list, and the exact order statistics are selected from that
-// list.  Every failure mode (bracket missed, list overflow) is detected exactly -- below <= rank <
-// below + candidates -- and falls back to the three-pass method, so the result is always the exact median.
-// lanes: like k_hist, 4 channels x 64 rows per step, 8 loads in flight per thread.
-// Candidates are staged in shared memory, kSlots private slots per thread (no atomics while collecting: a
-// global atomic per candidate serialised on the per-channel counters, 4.6 ms; a shared atomic per candidate
-// with its return value on the critical path, 0.75 ms), and flushed every kFlushIters steps: the threads of a
-// channel take their offsets from one shared counter, ONE global atomic per channel reserves the block's
-// range in the list.  A thread whose slots are full appends straight to the global list; a channel whose
-// list is already full (the bracket was useless: the caller will fall back) stops collecting, so a
-// degenerate input costs a bounded amount.
-constexpr int kFlushIters = 32, kSlots = 32;
-__global__ void __launch_bounds__(256) k_window(const float2* __restrict__ y, long long nrows, int M,
-                                                const SelState* __restrict__ win, unsigned long long* __restrict__ below,
-                                                uint32_t* __restrict__ cand_cnt, uint32_t* __restrict__ cand, uint32_t cap) {
-  __shared__ uint32_t stage[kSlots][256];          // [slot][thread]: conflict-free
-  __shared__ uint32_t scnt[4], sbase[4], sdead[4];
-  const int cl = threadIdx.x & 3, ch = blockIdx.x * 4 + cl;
-  const bool ch_ok = ch < M;
-  uint32_t lo = 1u, hi = 0u;                       // empty window for the padding channels of the last block
-  if (ch_ok) { lo = win[ch].prefix[0]; hi = win[ch].prefix[1]; }
-  if (threadIdx.x < 4) { scnt[threadIdx.x] = 0; sdead[threadIdx.x] = 0; }
-  __syncthreads();
-  const long long rows_per_block = (nrows + gridDim.y - 1) / gridDim.y;
-  const long long r_begin = (long long)blockIdx.y * rows_per_block;
-  long long r_end = r_begin + rows_per_block;
-  if (r_end > nrows) r_end = nrows;
-  unsigned long long nbelow = 0;
-  uint32_t* const mine = cand + (size_t)(ch_ok ? ch : 0) * cap;
-  constexpr int UN = 8;
-  int it = 0;
-  uint32_t nst = 0;                                // keys in this thread's slots
-  bool dead = false;
-  for (long long r0 = r_begin; r0 < r_end; r0 += 64 * UN) {        // block-uniform loop
-    const long long r = r0 + (threadIdx.x >> 2);
-    float2 v[UN];
-    #pragma unroll
-    for (int u = 0; u < UN; u++) {
-      const long long rr = r + 64LL * u;
-      v[u] = (ch_ok && rr < r_end) ? __ldg(y + rr * M + ch) : make_float2(0.f, 0.f);
-    }
-    #pragma unroll
-    for (int u = 0; u < UN; u++) {
-      if (!ch_ok || r + 64LL * u >= r_end) continue;
-      const uint32_t bits = __float_as_uint(mag_of(v[u]));
-      if (bits < lo) nbelow++;
-      else if (bits <= hi && !dead) {
-        if (nst < (uint32_t)kSlots) stage[nst++][threadIdx.x] = bits;
-        else {                                      // slots full: straight to the global list
-          const uint32_t idx = atomicAdd(&cand_cnt[ch], 1u);
-          if (idx < cap) mine[idx] = bits;
-        }
-      }
-    }
-    if (++it == kFlushIters || r0 + 64 * UN >= r_end) {
-      it = 0;
-      const uint32_t off = nst ? atomicAdd(&scnt[cl], nst) : 0u;    // offset inside the block's range of this channel
-      __syncthreads();
-      if (threadIdx.x < 4 && blockIdx.x * 4 + threadIdx.x < M) {
-        const uint32_t n = scnt[threadIdx.x];
-        const uint32_t base = n ? atomicAdd(&cand_cnt[blockIdx.x * 4 + threadIdx.x], n) : cand_cnt[blockIdx.x * 4 + threadIdx.x];
-        sbase[threadIdx.x] = base;
-        if (base + n > cap) sdead[threadIdx.x] = 1;  // this channel's list has overflowed: the median attempt will fall back
-      }
-      __syncthreads();
-      const uint32_t base = sbase[cl] + off;
-      for (uint32_t i = 0; i < nst; i++)
-        if (base + i < cap) mine[base + i] = stage[i][threadIdx.x];
-      nst = 0;
-      dead = sdead[cl] != 0;
-      __syncthreads();
-      if (threadIdx.x < 4) scnt[threadIdx.x] = 0;
-      __syncthreads();
-    }
-  }
-  if (nbelow) atomicAdd(&below[ch], nbelow);
 }
 
 // ---- edge detection -----------------------------------------------------------------------------------
@@ -372,30 +288,18 @@ __device__ void block_select2(KeyF key, unsigned long long n, unsigned long long
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { h0[i] = 0; h1[i] = 0; }
     __syncthreads();
     const bool split = pre[0] != pre[1];
-    constexpr int UNK = 4;                                   // keys fetched ahead (they may come from global memory)
-    for (unsigned long long i0 = threadIdx.x; i0 < n_up; i0 += (unsigned long long)UNK * blockDim.x) {
-      uint32_t kk[UNK];
-      #pragma unroll
-      for (int u = 0; u < UNK; u++) {
-        const unsigned long long i = i0 + (unsigned long long)u * blockDim.x;
-        kk[u] = i < n ? key(i) : 0u;
+    for (unsigned long long i = threadIdx.x; i < n_up; i += blockDim.x) {
+      int b0 = -1, b1 = -1;
+      if (i < n) {
+        const uint32_t k = key(i);
+        if ((k & pmask) == pre[0]) b0 = (int)((k >> shift) & 0xFF);
+        if (split && (k & pmask) == pre[1]) b1 = (int)((k >> shift) & 0xFF);
       }
-      #pragma unroll
-      for (int u = 0; u < UNK; u++) {
-        const unsigned long long i = i0 + (unsigned long long)u * blockDim.x;
-        if (i >= n_up) break;                                // warp-uniform: n_up is a multiple of blockDim.x
-        int b0 = -1, b1 = -1;
-        if (i < n) {
-          const uint32_t k = kk[u];
-          if ((k & pmask) == pre[0]) b0 = (int)((k >> shift) & 0xFF);
-          if (split && (k & pmask) == pre[1]) b1 = (int)((k >> shift) & 0xFF);
-        }
-        const unsigned m0 = __match_any_sync(0xffffffffu, b0);
-        if (b0 >= 0 && lane == __ffs(m0) - 1) atomicAdd(&h0[b0], (uint32_t)__popc(m0));
-        if (split) {                                         // block-uniform
-          const unsigned m1 = __match_any_sync(0xffffffffu, b1);
-          if (b1 >= 0 && lane == __ffs(m1) - 1) atomicAdd(&h1[b1], (uint32_t)__popc(m1));
-        }
+      const unsigned m0 = __match_any_sync(0xffffffffu, b0);
+      if (b0 >= 0 && lane == __ffs(m0) - 1) atomicAdd(&h0[b0], (uint32_t)__popc(m0));
+      if (split) {                                           // block-uniform
+        const unsigned m1 = __match_any_sync(0xffffffffu, b1);
+        if (b1 >= 0 && lane == __ffs(m1) - 1) atomicAdd(&h1[b1], (uint32_t)__popc(m1));
       }
     }
     __syncthreads();
@@ -432,28 +336,6 @@ __device__ void block_select2(KeyF key, unsigned long long n, unsigned long long
   }
   if (threadIdx.x == 0) { out[0] = pre[0]; out[1] = pre[1]; }
   __syncthreads();
-}
-
-// one block per channel: exact order statistics (ranks of the WHOLE channel) from the candidate list
-__global__ void __launch_bounds__(1024) k_cand_select(const uint32_t* __restrict__ cand, const uint32_t* __restrict__ cand_cnt,
-                                                     const unsigned long long* __restrict__ below, uint32_t cap,
-                                                     unsigned long long rank_lo, unsigned long long rank_hi,
-                                                     SelState* __restrict__ st, int* __restrict__ fail) {
-  __shared__ uint32_t h0[256], h1[256], res[2];
-  __shared__ unsigned long long sh_rank[2];
-  const int ch = blockIdx.x;
-  const unsigned long long n = cand_cnt[ch], b = below[ch];
-  if (n > cap || rank_lo < b || rank_hi >= b + n) {          // block-uniform: bracket missed or list overflowed
-    if (threadIdx.x == 0) atomicExch(fail, 1);
-    return;
-  }
-  const uint32_t* c = cand + (size_t)ch * cap;
-  block_select2([&](unsigned long long i) { return c[i]; }, n, rank_lo - b, rank_hi - b, h0, h1, res, sh_rank);
-  if (threadIdx.x == 0) {
-    SelState s;
-    s.prefix[0] = res[0]; s.prefix[1] = res[1]; s.rank[0] = 0; s.rank[1] = 0;
-    st[ch] = s;
-  }
 }
 
 constexpr int kPulseCap = 5632;   // rows of a pulse held in shared memory (8 B per row: 44 KB)
@@ -524,7 +406,7 @@ static int pdw_buffers(::chz* h) {
 }
 
 // local histogram of one radix pass (:73); pass 0 clears the table first (k_select clears it after every pass)
-static int pdw_hist_pass(::chz* h, const float2* y, uint64_t nrows, int pass, uint64_t row_stride = 1) {
+static int pdw_hist_pass(::chz* h, const float2* y, uint64_t nrows, int pass) {
   const int M = (int)h->M;
   cudaStream_t st = h->stream;
   int rc = pdw_buffers(h);
@@ -537,8 +419,7 @@ static int pdw_hist_pass(::chz* h, const float2* y, uint64_t nrows, int pass, ui
   if (ychunks > max_chunks) ychunks = max_chunks;
   if (ychunks < 1) ychunks = 1;
   if (ychunks > 65535) ychunks = 65535;
-  k_hist<<<dim3((M + 3) / 4, (unsigned)ychunks), 256, 0, st>>>(y, (long long)nrows, M, pass, (const SelState*)h->pdw_sel.p, d_hist,
-                                                                (long long)row_stride);
+  k_hist<<<dim3((M + 3) / 4, (unsigned)ychunks), 256, 0, st>>>(y, (long long)nrows, M, pass, (const SelState*)h->pdw_sel.p, d_hist);
   h->launches++;
   CHZ_CUDA(cudaGetLastError());
   return CHZ_OK;
@@ -546,66 +427,12 @@ static int pdw_hist_pass(::chz* h, const float2* y, uint64_t nrows, int pass, ui
 
 // fix the next bits of both middle order statistics from the (summed) histogram; total_rows = rows of the
 // WHOLE recording
-static int pdw_select_pass(::chz* h, int pass, uint64_t total_rows, int64_t spread = 0) {
+static int pdw_select_pass(::chz* h, int pass, uint64_t total_rows) {
   if (total_rows == 0 || total_rows > 0xFFFFFFFFull) return CHZ_EINVAL;
-  // spread > 0: the order statistics `spread` ranks below / above the middle (bracket of the sampled median)
-  int64_t lo = (int64_t)((total_rows - 1) / 2) - spread, hi = (int64_t)(total_rows / 2) + spread;
-  if (lo < 0) lo = 0;
-  if (hi > (int64_t)total_rows - 1) hi = (int64_t)total_rows - 1;
-  const uint32_t rank_lo = (uint32_t)lo, rank_hi = (uint32_t)hi;
+  const uint32_t rank_lo = (uint32_t)((total_rows - 1) / 2), rank_hi = (uint32_t)(total_rows / 2);
   k_select<<<h->M, 256, 0, h->stream>>>((uint32_t*)h->pdw_hist.p, (SelState*)h->pdw_sel.p, pass, rank_lo, rank_hi);
   h->launches++;
   CHZ_CUDA(cudaGetLastError());
-  return CHZ_OK;
-}
-
-// Exact per-channel median of |y| (:73) into pdw_sel: one full pass when the input is large (see k_window),
-// three radix passes otherwise or when the one-pass attempt reports a miss.
-static int pdw_median(::chz* h, const float2* y, uint64_t nrows) {
-  const int M = (int)h->M;
-  cudaStream_t st = h->stream;
-  int rc;
-  constexpr uint64_t kStride = 61, kMinRows = 1u << 17;
-  static const bool off = std::getenv("CHZ_PDW_THREE_PASS") != nullptr;     // A/B and debugging aid
-  if (!off && !h->pdw_three_pass && nrows >= kMinRows && nrows <= 0xFFFFFFFFull) {
-    const uint64_t ns = (nrows + kStride - 1) / kStride;
-    const int64_t spread = (int64_t)std::ceil(4.0 * std::sqrt((double)ns)) + 2;
-    // candidates expected per channel: the bracket spans 2*spread+2 of ns sample ranks
-    const double expect = (double)nrows * (double)(2 * spread + 2) / (double)ns;
-    const uint64_t cap = (uint64_t)(2.5 * expect) + 4096;
-    if (cap <= 0xFFFFFFFFull && (double)cap * M * 4.0 <= 1.0e9) {
-      for (int pass = 0; pass < 3; pass++) {
-        if ((rc = pdw_hist_pass(h, y, ns, pass, kStride))) return rc;
-        if ((rc = pdw_select_pass(h, pass, ns, spread))) return rc;
-      }
-      const size_t head = (size_t)M * (sizeof(unsigned long long) + sizeof(uint32_t)) + 16;
-      CHZ_CUDA(h->pdw_cand.reserve(head + (size_t)M * cap * sizeof(uint32_t)));
-      unsigned long long* d_below = (unsigned long long*)h->pdw_cand.p;
-      uint32_t* d_cnt = (uint32_t*)(d_below + M);
-      int* d_fail = (int*)(d_cnt + M);
-      uint32_t* d_cand = (uint32_t*)((char*)h->pdw_cand.p + ((head + 15) / 16) * 16);
-      CHZ_CUDA(cudaMemsetAsync(h->pdw_cand.p, 0, head, st));
-      long long ychunks = (h->sm_count * 4 + (M + 3) / 4 - 1) / ((M + 3) / 4);
-      const long long max_chunks = (long long)((nrows + 255) / 256);
-      if (ychunks > max_chunks) ychunks = max_chunks;
-      if (ychunks < 1) ychunks = 1;
-      if (ychunks > 65535) ychunks = 65535;
-      k_window<<<dim3((M + 3) / 4, (unsigned)ychunks), 256, 0, st>>>(y, (long long)nrows, M, (const SelState*)h->pdw_sel.p, d_below,
-                                                                      d_cnt, d_cand, (uint32_t)cap);
-      k_cand_select<<<M, 1024, 0, st>>>(d_cand, d_cnt, d_below, (uint32_t)cap, (nrows - 1) / 2, nrows / 2, (SelState*)h->pdw_sel.p, d_fail);
-      h->launches += 2;
-      CHZ_CUDA(cudaGetLastError());
-      int fail = 0;
-      CHZ_CUDA(cudaMemcpyAsync(&fail, d_fail, sizeof fail, cudaMemcpyDeviceToHost, st));
-      CHZ_CUDA(cudaStreamSynchronize(st));
-      if (!fail) return CHZ_OK;
-      h->median_fallbacks++;
-    }
-  }
-  for (int pass = 0; pass < 3; pass++) {
-    if ((rc = pdw_hist_pass(h, y, nrows, pass))) return rc;
-    if ((rc = pdw_select_pass(h, pass, nrows))) return rc;
-  }
   return CHZ_OK;
 }
 
@@ -797,7 +624,10 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
   if (nrows == 0) return CHZ_OK;
   int rc;
   // 1. exact per-channel median of |y| (:73)
-  if ((rc = pdw_median(h, y, nrows))) return rc;
+  for (int pass = 0; pass < 3; pass++) {
+    if ((rc = pdw_hist_pass(h, y, nrows, pass))) return rc;
+    if ((rc = pdw_select_pass(h, pass, nrows))) return rc;
+  }
   lap("median");
   // 2. thresholds (:74-75)
   if ((rc = pdw_thresholds(h, prm, false))) return rc;

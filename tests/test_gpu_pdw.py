@@ -396,55 +396,3 @@ def test_sharded_pdws_hysteresis_across_boundaries():
         for recs, nfs in _sharded_on_one_gpu(y, bounds, 1e6, **kw):
             _same_records(recs, whole)
             assert np.array_equal(nfs, nf)
-
-
-# ---- one-pass exact median for large inputs (sampled bracket + candidate list) --------------------------
-def _pdws_median_modes(y, fs, **kw):
-    """-> [(records, noise floor, median-stage kernel launches)] for the automatic and the forced three-pass median."""
-    torch = _torch()
-    from sdr_channelizer_b200 import _lib
-    M = y.shape[1]
-    d = torch.from_numpy(np.ascontiguousarray(y.astype(np.complex64))).cuda()
-    out = []
-    for three in (0, 1):
-        ch = pkg.Channelizer(M, NumTapsPerBand=8) if M > 1 else pkg.Channelizer(1, taps=np.ones(1, np.float32))
-        ch.set_option(_lib.CHZ_OPT_PDW_THREE_PASS, three)
-        ch.set_stream(torch.cuda.current_stream().cuda_stream)
-        l0 = ch.kernel_launches
-        recs, nf = ch.pdws_ptr(d.data_ptr(), y.shape[0], fs, **kw)
-        out.append((recs, nf, ch.kernel_launches - l0))
-        ch.close()
-    return out
-
-
-def test_one_pass_median_equals_three_pass_and_oracle(orc):
-    """>= 2^17 rows: the noise floor comes from ONE full pass (bracket from a 1/61 row subsample, candidates,
-    exact select) and must equal the three-pass result bit for bit; records byte-identical; oracle medians."""
-    rng = np.random.default_rng(8)
-    rows, M = 200_000, 8
-    y = ((rng.normal(size=(rows, M)) + 1j * rng.normal(size=(rows, M))) * (0.01 * (1 + np.arange(M)))).astype(np.complex64)
-    y[5000:5400, 1] += 2.0; y[150_000:150_900, 6] += 3.0 * np.exp(2j * np.pi * 0.01 * np.arange(900))
-    y[::2, 7] *= 0.5                                                          # a channel with a bimodal magnitude distribution
-    (r1, nf1, l1), (r3, nf3, l3) = _pdws_median_modes(y, 8e6)
-    assert l1 - l3 == 2 and len(r1) >= 2               # 6 sampled + window + select against 6 launches: no fall-back happened
-    assert np.array_equal(nf1, nf3)
-    _same_records(r1, r3)
-    onf = np.median(np.abs(y.astype(np.complex128)), axis=0)
-    assert np.allclose(nf1, onf, rtol=3e-7)
-
-
-def test_one_pass_median_falls_back_exactly():
-    """Inputs that defeat the sampled bracket: a channel that is constant (every value is a candidate: the list
-    overflows) and one whose every 61st row -- exactly the subsample -- is an outlier (the bracket misses the
-    true median).  Both are detected exactly and the three radix passes run instead."""
-    rng = np.random.default_rng(9)
-    rows, M = 140_000, 4
-    y = ((rng.normal(size=(rows, M)) + 1j * rng.normal(size=(rows, M))) * 0.01).astype(np.complex64)
-    y[:, 2] = np.where(np.arange(rows) % 2 == 0, 0.25, 0.5)                   # two values: every row is a candidate
-    (r1, nf1, l1), (r3, nf3, l3) = _pdws_median_modes(y, 4e6)
-    assert l1 - l3 == 8 and np.array_equal(nf1, nf3) and nf1[2] == 0.375      # one-pass attempt (8 launches) + the three passes
-    y[:, 2] = y[:, 1]
-    y[::61, 3] = 5.0
-    (r1, nf1, l1), (r3, nf3, l3) = _pdws_median_modes(y, 4e6)
-    assert l1 - l3 == 8 and np.array_equal(nf1, nf3)
-    _same_records(r1, r3)
