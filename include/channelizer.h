@@ -111,7 +111,11 @@ int chz_set_stream(chz_t* h, void* cuda_stream);
 /* Options (chz_set_option) */
 #define CHZ_OPT_RETAIN        1  /* 1 (default): chz_process keeps its output rows on the device for chz_pdws */
 #define CHZ_OPT_CHUNK_ROWS    2  /* host path: rows per pipelined H2D/compute/D2H chunk (0 = auto) */
-#define CHZ_OPT_FORCE_PATH    3  /* 0 auto, 1 fused kernel, 2 split FIR + row-FFT kernels, 3 cluster kernel with an L2 ring (M >= 1024), 4 warp-specialised kernel (M = 64), 5 CTA-pair DSMEM kernel (M = 1024), 6 pipelined FIR+FFT task-queue kernel (M >= 1024), 7/8/9 L2-ring cluster kernel with 256-thread CTAs / + split arrive-wait pipelining / 512-thread pipelined, 10 DSMEM st.async cluster kernel; 3-10 are experiments measured slower than (or within 3 % of) the default, see DESIGN.md */
+#define CHZ_OPT_FORCE_PATH    3  /* kernel family: 0 auto (default), 1 fused kernel (M <= 560), 2 split FIR + row-FFT kernels,
+                                    11 fused ring kernel (M = 1024: TMA-fed raw-sample ring, in-place FFT).  3-10 are the
+                                    round-1 large-M / warp-specialisation experiments, present only in a `make EXPERIMENTS=1`
+                                    build.  A path that is not built, or has no kernel for the handle's
+                                    (M, taps), is refused with CHZ_EINVAL. */
 int chz_set_option(chz_t* h, int opt, int64_t value);
 
 uint32_t chz_num_channels(const chz_t* h);

@@ -240,8 +240,13 @@ static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, 
     const bool dsm = dsm_available(h) && h->force_path == 10;
     if (h->force_path == 10 && !dsm) return CHZ_EINVAL;
     const bool pipe = pipe_available(h) && h->force_path == 6;
+    const bool ringp = ring_available(h) && (h->force_path == 0 || h->force_path == 11);
+    if (h->force_path == 11 && !ringp) return CHZ_EINVAL;
     if (h->force_path == 6 && !pipe) return CHZ_EINVAL;
-    if (dsm) {
+    if (ringp) {
+      rc = launch_ring_any(h, prm, in16, st);
+      if (rc) return rc == 1 ? CHZ_EINVAL : rc;
+    } else if (dsm) {
       rc = launch_dsm_any(h, prm, in16, st);
       if (rc) return rc == 1 ? CHZ_EINVAL : rc;
     } else if (pipe) {
@@ -495,6 +500,17 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
       ns *= R;
     }
   }
+  {
+    std::vector<float2> twn(M);
+    for (uint32_t i = 0; i < M; i++) {
+      const double a = 2.0 * 3.14159265358979323846264338327950288 * (double)i / (double)M;
+      twn[i] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    CHZ_TRY(cudaMalloc(&h->d_twn, sizeof(float2) * M));
+    CHZ_TRY(cudaMemcpy(h->d_twn, twn.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+  }
+  if (const char* e = std::getenv("CHZ_RING_UNPACK")) h->ring_unpack = std::atoi(e);          // tuning aids
+  if (const char* e = std::getenv("CHZ_RING_MIN_STEPS")) { const int v = std::atoi(e); if (v > 0) h->ring_min_steps = v; }
   CHZ_TRY(cudaMalloc(&h->d_tw, sizeof(float2) * M));
   CHZ_TRY(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
   if (const char* e = std::getenv("CHZ_SPLIT_OVERLAP")) h->split_overlap = std::atoi(e) != 0;   // tuning aid
@@ -521,6 +537,7 @@ void chz_destroy(chz_t* h) {
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   for (int i = 0; i < 17; i++) if (h->d_taps[i]) cudaFree(h->d_taps[i]);
   if (h->d_tw) cudaFree(h->d_tw);
+  if (h->d_twn) cudaFree(h->d_twn);
   for (int i = 0; i < 2; i++) {
     if (h->d_hist[i]) cudaFree(h->d_hist[i]);
     if (h->d_in[i]) cudaFree(h->d_in[i]);
@@ -563,7 +580,24 @@ int chz_set_option(chz_t* h, int opt, int64_t value) {
   switch (opt) {
     case CHZ_OPT_RETAIN: h->retain = value != 0; return CHZ_OK;
     case CHZ_OPT_CHUNK_ROWS: if (value < 0) return CHZ_EINVAL; h->chunk_rows = value; return CHZ_OK;
-    case CHZ_OPT_FORCE_PATH: if (value < 0 || value > 10) return CHZ_EINVAL; h->force_path = (int)value; return CHZ_OK;
+    case CHZ_OPT_FORCE_PATH: {
+      bool ok = false;   // a path this build does not contain, or that has no kernel for the handle's (M, taps), is refused here
+      switch (value) {
+        case 0: case 2: ok = true; break;
+        case 1: ok = fused_available(h); break;
+        case 3: case 9: ok = cluster_available(h, 512); break;
+        case 7: case 8: ok = cluster_available(h, 256); break;
+        case 4: ok = ws_available(h); break;
+        case 5: ok = dit2_available(h); break;
+        case 6: ok = pipe_available(h); break;
+        case 10: ok = dsm_available(h); break;
+        case 11: ok = ring_available(h); break;
+        default: break;
+      }
+      if (!ok) return CHZ_EINVAL;
+      h->force_path = (int)value;
+      return CHZ_OK;
+    }
     default: return CHZ_EINVAL;
   }
 }

@@ -13,8 +13,18 @@ namespace chzi {
 // ---- complex helpers (float2 = re,im).  __f*2_rn map to the packed FADD2/FMUL2/FFMA2 of sm_100 ----
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a*w in packed form: FMUL2 (a.x broadcast) + FFMA2 (a.y broadcast, w with its halves swapped and one sign
+// flipped) = 3 FMA-pipe instructions including the sign flip; every FMA-pipe instruction, scalar or packed,
+// occupies the pipe for two cycles on sm_100, so the scalar form below (2 FMUL + 2 FFMA) costs 4.
+__device__ __forceinline__ float2 cmul_p(float2 a, float2 w) {
+  return __ffma2_rn(make_float2(a.y, a.y), make_float2(-w.y, w.x), __fmul2_rn(make_float2(a.x, a.x), w));
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) {   // a*w
+#ifdef CHZ_CMUL_PACKED
+  return cmul_p(a, w);
+#else
   return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+#endif
 }
 __device__ __forceinline__ float2 mul_j(float2 a) { return make_float2(-a.y, a.x); }    // * (+j)
 

@@ -50,7 +50,9 @@ struct chz {
   int fir_bpb = 0;                      // register-window FIR block size for run-time M (0 = direct FIR kernel)
   std::vector<float> taps;              // prototype as given (unscaled), h[qM + p]
   float* d_taps[17] = {nullptr};        // per bit width: taps * 2^-(bw-1), uploaded on first use
-  float2* d_tw = nullptr;               // e^{+j 2 pi i / M}
+  float2* d_tw = nullptr;               // inter-pass twiddles of the Stockham plan (per-pass layout, chz_create)
+  float2* d_twn = nullptr;              // plain table e^{+j 2 pi i / M}, i < M (ring kernel)
+  int ring_min_steps = 4, ring_unpack = 0;   // ring kernel: 8-frame steps per CTA at least; unpack policy (CHZ_RING_UNPACK)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};

@@ -20,6 +20,8 @@ int launch_ws_any(::chz* h, const ChanParams& prm, bool in16, cudaStream_t st);
 int launch_cluster_any(::chz* h, const ChanParams& prm, bool in16, int path, cudaStream_t st);   // path 3, 7, 8 or 9
 int launch_dsm_any(::chz* h, const ChanParams& prm, bool in16, cudaStream_t st);
 int launch_pipe_any(::chz* h, const ChanParams& prm, bool in16, cudaStream_t st);
+int launch_ring_any(::chz* h, const ChanParams& prm, bool in16, cudaStream_t st);      // chz_launch_ring.cu
+bool ring_available(const ::chz* h);
 bool dit2_available(const ::chz* h);
 bool ws_available(const ::chz* h);
 bool cluster_available(const ::chz* h, int tpc);

@@ -6,8 +6,10 @@
 #include <cstring>
 
 #include "chz_internal.h"
-#include "chz_kernels.cuh"
 #include "chz_launch.h"
+
+#ifdef CHZ_EXPERIMENTS
+#include "chz_kernels_exp.cuh"
 
 namespace chzi {
 
@@ -280,3 +282,21 @@ int launch_pipe_any(::chz* h, const ChanParams& prm, bool in16, cudaStream_t st)
 }
 
 }  // namespace chzi
+
+#else   // default build: the experiment kernels are not compiled; forcing one of their paths is CHZ_EINVAL
+
+namespace chzi {
+struct ChanParams;
+bool dit2_available(const ::chz*) { return false; }
+bool ws_available(const ::chz*) { return false; }
+bool cluster_available(const ::chz*, int) { return false; }
+bool dsm_available(const ::chz*) { return false; }
+bool pipe_available(const ::chz*) { return false; }
+int launch_dit2_any(::chz*, const ChanParams&, bool, cudaStream_t) { return 1; }
+int launch_ws_any(::chz*, const ChanParams&, bool, cudaStream_t) { return 1; }
+int launch_cluster_any(::chz*, const ChanParams&, bool, int, cudaStream_t) { return 1; }
+int launch_dsm_any(::chz*, const ChanParams&, bool, cudaStream_t) { return 1; }
+int launch_pipe_any(::chz*, const ChanParams&, bool, cudaStream_t) { return 1; }
+}  // namespace chzi
+
+#endif

@@ -1,0 +1,56 @@
+// Launcher of the large-M fused ring kernel (k_chan_ring, chz_ring.cuh): M = 1024, P in {8, 12, 16}.
+#include <algorithm>
+#include <cstdlib>
+
+#include "chz_internal.h"
+#include "chz_ring.cuh"
+#include "chz_launch.h"
+
+namespace chzi {
+
+template <int P, bool IN16, int UNPACK>
+static int launch_ring(::chz* h, const ChanParams& prm, cudaStream_t st) {
+  typedef ring::Smem<IN16> SM;
+  auto kern = ring::k_chan_ring<P, IN16, UNPACK>;
+  static thread_local bool attr_dev[kMaxDev] = {false};
+  bool& attr = attr_dev[h->device % kMaxDev];
+  if (!attr) {
+    CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr = true;
+  }
+  ring::RingParams rp;
+  const long long os = prm.os;
+  rp.a_lo = prm.row_base / os;
+  const long long a_hi = (prm.row_base + prm.nrows - 1) / os + 1;
+  rp.nsteps = (a_hi - rp.a_lo + ring::kR - 1) / ring::kR;
+  rp.twn = h->d_twn;
+  // one persistent CTA per SM; a CTA's run starts with a 16-frame warm-up, so short calls use fewer CTAs
+  long long grid = std::min<long long>(h->sm_count, std::max<long long>(1, rp.nsteps / h->ring_min_steps));
+  kern<<<(unsigned)grid, ring::kNT, SM::TOTAL, st>>>(prm, rp);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  return CHZ_OK;
+}
+
+template <bool IN16, int UNPACK>
+static int launch_ring_p(::chz* h, const ChanParams& prm, cudaStream_t st) {
+  switch (h->P) {
+    case 8: return launch_ring<8, IN16, UNPACK>(h, prm, st);
+    case 12: return launch_ring<12, IN16, UNPACK>(h, prm, st);
+    case 16: return launch_ring<16, IN16, UNPACK>(h, prm, st);
+    default: return 1;
+  }
+}
+
+bool ring_available(const ::chz* h) { return !h->generic && h->M == 1024 && (h->P == 8 || h->P == 12 || h->P == 16); }
+
+int launch_ring_any(::chz* h, const ChanParams& prm, bool in16, cudaStream_t st) {
+  if (!ring_available(h)) return 1;
+  switch (h->ring_unpack) {
+    case 1: return in16 ? launch_ring_p<true, 1>(h, prm, st) : launch_ring_p<false, 1>(h, prm, st);
+    case 2: return in16 ? launch_ring_p<true, 2>(h, prm, st) : launch_ring_p<false, 2>(h, prm, st);
+    default: return in16 ? launch_ring_p<true, 0>(h, prm, st) : launch_ring_p<false, 0>(h, prm, st);
+  }
+}
+
+}  // namespace chzi

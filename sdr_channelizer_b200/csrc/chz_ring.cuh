@@ -1,0 +1,289 @@
+// Fused K1+K2+K3 for large channel counts (M = 1024 per CTA): one global read of the raw samples, one
+// global write of the channel rows -- the path the split FIR + FFT kernels cannot reach (they move the
+// fp32 FIR output to DRAM and back: 28 B per sample against 12 algorithmic).
+// Reference math replaced: matlab/create_pdws_channelized.m:35-38 (normalise) and :57 (channelizer(iq)).
+//
+// One persistent CTA per SM owns a contiguous run of the recording.  On chip it keeps
+//   * a ring of the last 24 raw frames A_a = x[aM, aM+M) (int16 pairs as recorded, 4 KB each), fed by
+//     cp.async.bulk (TMA, mbarrier completion) eight frames at a time while the FFT of the previous eight runs;
+//   * the P taps of two polyphase branches per thread in registers;
+//   * one tile of 8 output rows x M channels (fp32 complex) on which the M-point FFT runs IN PLACE.
+// Per step a thread reads the P+7 raw words of its two branches once from the ring, unpacks them and feeds
+// eight running sums per branch (no re-reads of the recording from L2: DRAM and L2 see every sample once),
+// the CTA then runs a decimation-in-frequency FFT 8 x 8 x 16 whose last pass streams the rows to global memory
+// with the lanes across channels (whole 256-byte runs per store).  2x oversampling = the same step run twice
+// per ring advance: the odd rows read the ring half a frame later and rotate the branches by M/2.
+#pragma once
+#include "chz_kernels.cuh"
+
+namespace chzi {
+namespace ring {
+
+constexpr int kM = 1024;        // channels = branches per CTA
+constexpr int kNT = 512;        // threads: two adjacent branches each
+constexpr int kR = 8;           // output rows per tile = frames per ring slot
+constexpr int kSlots = 3;       // ring = 3 slots of 8 frames: rows a0-16 .. a0+7 of the step at a0
+constexpr int kTileStride = kM + 2 * (kM / 128);   // float2 per tile row: 2 pad elements per 128 (see pass 2)
+
+struct RingParams {
+  long long a_lo;       // first frame whose rows this launch produces (row m = os*a + phase)
+  long long nsteps;     // steps of 8 frames over all CTAs
+  const float2* twn;    // e^{+j 2 pi i / M}, i < M
+};
+
+template <bool IN16> struct Smem {
+  typedef typename RawT<IN16>::type raw_t;
+  static constexpr int ROWB = kM * (int)sizeof(raw_t);            // bytes per frame
+  static constexpr int SLOTB = kR * ROWB;                         // bytes per ring slot
+  static constexpr int RING = kSlots * SLOTB;
+  static constexpr int TILE = kR * kTileStride * (int)sizeof(float2);
+  static constexpr int OFF_TILE = RING;
+  static constexpr int OFF_H0 = OFF_TILE + TILE;                  // taps of branch 0 (32 floats)
+  static constexpr int OFF_TW1 = OFF_H0 + 32 * (int)sizeof(float);   // pass-1 twiddles W_128^{j1 k}: [7][16] float2
+  static constexpr int OFF_BAR = OFF_TW1 + 7 * 16 * (int)sizeof(float2);
+  static constexpr int TOTAL = OFF_BAR + 16;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// Unpack policies for one raw word (int16 I | int16 Q << 16, or int8 pair) -> integer-valued float2.
+//   0: two I2F (conversion pipe)   1: I2F for I, shift + I2FP (ALU pipe) for Q   2: sign-extend + I2FP for both
+template <bool IN16, int UNPACK>
+__device__ __forceinline__ float2 unpack(uint32_t raw) {
+  if (!IN16) {
+    if (UNPACK == 0) return unpack_raw<false>(raw);
+    const int q = ((int)(raw << 16)) >> 24, i = ((int)(raw << 24)) >> 24;
+    return make_float2(__int2float_rn(i), __int2float_rn(q));
+  }
+  if (UNPACK == 0) return unpack_raw<true>(raw);
+  const int q = ((int)raw) >> 16;
+  if (UNPACK == 1) return make_float2((float)(short)(raw & 0xffffu), __int2float_rn(q));
+  const int i = ((int)(raw << 16)) >> 16;
+  return make_float2(__int2float_rn(i), __int2float_rn(q));
+}
+
+// tile element index of channel position pos: two pad elements per 128 so that the eight lanes of a
+// quarter-warp that read 16-byte pieces of eight different 128-blocks in pass 2 hit distinct banks
+__device__ __forceinline__ int tpad(int pos) { return pos + ((pos >> 7) << 1); }
+
+template <int P, bool IN16, int UNPACK>
+__global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams rp) {
+  typedef Smem<IN16> SM;
+  typedef typename RawT<IN16>::type raw_t;
+  constexpr int M = kM, ROWB = SM::ROWB, SLOTB = SM::SLOTB, TS = kTileStride;
+  constexpr int J0 = 16 - P;                      // first ring row (relative to a0-16) a delta = 0 thread reads
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2* tile = (float2*)(smem + SM::OFF_TILE);
+  float* h0s = (float*)(smem + SM::OFF_H0);
+  float2* tw1s = (float2*)(smem + SM::OFF_TW1);
+  const unsigned ring_s = smem_u32(smem), bar = smem_u32(smem + SM::OFF_BAR);
+  const int t = threadIdx.x;
+  const int os = prm.os, D = prm.D;
+
+  // ---- this CTA's run of steps ----
+  const long long k0 = rp.nsteps * blockIdx.x / gridDim.x, k1 = rp.nsteps * (blockIdx.x + 1) / gridDim.x;
+  if (k0 >= k1) return;
+
+  // ---- persistent per-thread state: taps of branches 2t+1 and (2t+2) mod M, twiddles of passes 0 and 1 ----
+  const int b1 = 2 * t + 1, b2 = (2 * t + 2) & (M - 1);
+  float h1[P], h2[P];
+  #pragma unroll
+  for (int q = 0; q < P; q++) { h1[q] = __ldg(prm.taps + q * M + b1); h2[q] = __ldg(prm.taps + q * M + b2); }
+  if (t < P) h0s[t] = __ldg(prm.taps + t * M);
+  float2 tw0[7];
+  #pragma unroll
+  for (int k = 1; k < 8; k++) tw0[k - 1] = __ldg(rp.twn + (((t & 127) * k) & (M - 1)));   // W_M^{j k}, j = t mod 128
+  if (t < 7 * 16) tw1s[t] = __ldg(rp.twn + ((((t & 15) * ((t >> 4) + 1)) << 3) & (M - 1)));   // W_128^{j1 k} at [k-1][j1]
+  if (t == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long in_end = prm.in_base + prm.n_in;
+  // bulk copies need 16-byte aligned global addresses: frame starts are multiples of M samples from in_base
+  const bool aligned = ((((unsigned long long)prm.in) - (unsigned long long)prm.in_base * sizeof(raw_t)) & 15ull) == 0;
+  const raw_t* __restrict__ inp = (const raw_t*)prm.in - prm.in_base;   // inp[idx], idx in [in_base, in_end)
+  unsigned parity = 0;
+  bool pending = false;                           // a bulk copy into the newest slot is in flight
+
+  // frames [a, a+8) -> ring slot s.  Whole slot inside this call's input and aligned: one bulk copy issued by
+  // thread 0 (the caller waits on the mbarrier before reading); otherwise every thread copies with bounds
+  // checks (history buffer, zeros before the stream start and past the data) and the caller synchronises.
+  auto load_slot = [&](long long a, int s) -> bool {
+    const long long lo = a * M, hi = lo + (long long)kR * M;
+    if (aligned && lo >= prm.in_base && hi <= in_end) {
+      if (t == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, SLOTB);
+        bulk_g2s(ring_s + s * SLOTB, inp + lo, SLOTB, bar);
+      }
+      return true;
+    }
+    raw_t* dst = (raw_t*)(smem + s * SLOTB);
+    #pragma unroll 4
+    for (int e = t; e < kR * M; e += kNT) dst[e] = (raw_t)load_raw<IN16>(prm, lo + e);
+    return false;
+  };
+
+  const long long a_start = rp.a_lo + k0 * kR;
+  // warm-up: the 16 frames before the first step.  One bulk copy at a time on the single mbarrier, and a
+  // CTA barrier after every wait so that no thread can still be polling phase n when phase n + 1 completes.
+  if (load_slot(a_start - 2 * kR, 0)) { mbar_wait(bar, parity); parity ^= 1; }
+  __syncthreads();
+  if (load_slot(a_start - kR, 1)) { mbar_wait(bar, parity); parity ^= 1; }
+  __syncthreads();
+  pending = load_slot(a_start, 2);
+
+  int s_old = 0;                                   // slot of frames a0-16 .. a0-9
+  for (long long k = k0; k < k1; k++) {
+    const long long a0 = rp.a_lo + k * kR;
+    const int s_mid = s_old == 2 ? 0 : s_old + 1, s_new = s_mid == 2 ? 0 : s_mid + 1;
+    __syncthreads();                               // last step's pass 2 has read the tile; slow-path ring writes are visible
+    if (pending) { mbar_wait(bar, parity); parity ^= 1; }
+    const unsigned sb0 = ring_s + s_old * SLOTB, sb1 = ring_s + s_mid * SLOTB, sb2 = ring_s + s_new * SLOTB;
+
+    for (int ph = 0; ph < os; ph++) {
+      // ---- FIR: 8 rows x 2 branches per thread ----
+      // Row m = os*a + ph, branch p reads x[a M + ph D - q M - p] = frame (a - q - 1 + delta), column cl:
+      //   ph = 0: cl = M - p, delta = 0 (p >= 1);  ph = 1: p <= D: cl = D - p, delta = 1;  p > D: cl = M + D - p, delta = 0.
+      // The pair (2t+2, 2t+1) is the 8-byte aligned pair of columns (cl, cl + 1).  Branch 0 (thread 511's
+      // first element) is the one column whose delta differs from its neighbour's: fixed up below.
+      const bool lowhalf = ph && t < D / 2;
+      const int cl = ph ? (lowhalf ? D - 2 * t - 2 : M + D - 2 * t - 2) : M - 2 * t - 2;
+      const unsigned dcol = (unsigned)cl * sizeof(raw_t) + (lowhalf ? ROWB : 0);
+      const unsigned r0b = sb0 + dcol, r1b = sb1 + dcol, r2b = sb2 + dcol;
+      const unsigned e0 = lowhalf ? sb1 + cl * (unsigned)sizeof(raw_t) : sb0 + 7 * ROWB + cl * (unsigned)sizeof(raw_t);
+      const unsigned e1 = lowhalf ? sb2 + cl * (unsigned)sizeof(raw_t) : sb1 + 7 * ROWB + cl * (unsigned)sizeof(raw_t);
+      float2 acc1[kR], acc2[kR];
+      #pragma unroll
+      for (int r = 0; r < kR; r++) { acc1[r] = make_float2(0.f, 0.f); acc2[r] = make_float2(0.f, 0.f); }
+      #pragma unroll
+      for (int ii = 0; ii < P + kR - 1; ii++) {
+        const int j = ii + J0;                       // ring row (before delta), compile time
+        const unsigned addr = (j & 7) == 7 ? (j < 8 ? e0 : e1) : ((j < 8 ? r0b : (j < 16 ? r1b : r2b)) + (j & 7) * ROWB);
+        uint32_t wa, wb;                             // columns cl (branch 2t+2) and cl+1 (branch 2t+1)
+        if (IN16) {
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wa), "=r"(wb) : "r"(addr));
+        } else {
+          uint32_t w;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
+          wa = w & 0xffffu; wb = w >> 16;
+        }
+        const float2 xa = unpack<IN16, UNPACK>(wa), xb = unpack<IN16, UNPACK>(wb);
+        #pragma unroll
+        for (int r = 0; r < kR; r++) {
+          const int q = r + P - 1 - ii;
+          if (q >= 0 && q < P) {
+            acc2[r] = __ffma2_rn(make_float2(h2[q], h2[q]), xa, acc2[r]);
+            acc1[r] = __ffma2_rn(make_float2(h1[q], h1[q]), xb, acc1[r]);
+          }
+        }
+      }
+      const int shift = ph ? D : 0;
+      const int pos1 = tpad((b1 - shift) & (M - 1)), pos2 = tpad((b2 - shift) & (M - 1));
+      #pragma unroll
+      for (int r = 0; r < kR; r++) { tile[r * TS + pos1] = acc1[r]; tile[r * TS + pos2] = acc2[r]; }
+      if (t >= kNT - 32) {
+        // branch 0: u_0[m] = sum_q h[qM] x[a M + ph D - q M] = frame (a - q), column ph*D: rows 16 + r - q of the ring
+        __syncwarp();
+        const int r = t & 31;
+        if (r < kR) {
+          float2 acc = make_float2(0.f, 0.f);
+          const unsigned c0 = (unsigned)(ph ? D : 0) * sizeof(raw_t);
+          #pragma unroll
+          for (int q = P - 1; q >= 0; q--) {
+            const int i = 16 + r - q;                 // 1 .. 23
+            const unsigned sb = i < 8 ? sb0 : (i < 16 ? sb1 : sb2);
+            uint32_t w;
+            if (IN16) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sb + (i & 7) * ROWB + c0));
+            else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w) : "r"(sb + (i & 7) * ROWB + c0));
+            acc = __ffma2_rn(make_float2(h0s[q], h0s[q]), unpack<IN16, UNPACK>(w), acc);
+          }
+          tile[r * TS + tpad((0 - shift) & (M - 1))] = acc;
+        }
+      }
+      __syncthreads();
+      // the oldest slot is dead after the last phase's FIR: request the next step's frames into it now, the
+      // copy lands while the FFT passes run
+      if (ph == os - 1) pending = (k + 1 < k1) ? load_slot(a0 + kR, s_old) : false;
+
+      // ---- FFT, decimation in frequency, in place: 8 (stride 128) x 8 (stride 16) x 16 (contiguous) ----
+      {   // pass 0: z_{k0}[j] = W_M^{j k0} sum_q u[j + 128 q] W_8^{q k0}  ->  position 128 k0 + j
+        const int j = t & 127, rr = t >> 7;
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {
+          float2* row = tile + (rr + 4 * h) * TS + j;
+          float2 v[8];
+          #pragma unroll
+          for (int q = 0; q < 8; q++) v[q] = row[q * 130];
+          dft8(v);
+          #pragma unroll
+          for (int q = 1; q < 8; q++) v[q] = cmul_p(v[q], tw0[q - 1]);
+          #pragma unroll
+          for (int q = 0; q < 8; q++) row[q * 130] = v[q];
+        }
+      }
+      __syncthreads();
+      {   // pass 1 inside block k0: w_{k1}[j1] = W_128^{j1 k1} sum_q z[j1 + 16 q] W_8^{q k1}  ->  position 128 k0 + 16 k1 + j1
+        const int j1 = t & 15, kb = (t >> 4) & 7, rr = t >> 7;
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {
+          float2* row = tile + (rr + 4 * h) * TS + kb * 130 + j1;
+          float2 v[8];
+          #pragma unroll
+          for (int q = 0; q < 8; q++) v[q] = row[q * 16];
+          dft8(v);
+          #pragma unroll
+          for (int q = 1; q < 8; q++) v[q] = cmul_p(v[q], tw1s[(q - 1) * 16 + j1]);
+          #pragma unroll
+          for (int q = 0; q < 8; q++) row[q * 16] = v[q];
+        }
+      }
+      __syncthreads();
+      {   // pass 2: y[k0 + 8 k1 + 64 k2] = sum_{j1} w[j1] W_16^{j1 k2}; lanes run over (k0, k1): 32 consecutive channels per store
+        const int row_i = t >> 6, b = t & 63, kb = b & 7, kc = b >> 3;
+        const float4* src = (const float4*)(tile + row_i * TS + kb * 130 + kc * 16);
+        float2 v[16];
+        #pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const float4 f = src[q];
+          v[2 * q] = make_float2(f.x, f.y); v[2 * q + 1] = make_float2(f.z, f.w);
+        }
+        dft16(v);
+        const long long m = (a0 + row_i) * os + ph;
+        if (m >= prm.row_base && m < prm.row_base + prm.nrows) {
+          float2* g = prm.out + (m - prm.row_base) * (long long)M + b;
+          #pragma unroll
+          for (int q = 0; q < 16; q++) g[q * 64] = v[q];
+        }
+      }
+      if (ph + 1 < os) __syncthreads();             // the next phase's FIR overwrites the tile
+    }
+    s_old = s_mid;
+  }
+}
+
+}  // namespace ring
+}  // namespace chzi
