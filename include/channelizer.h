@@ -109,7 +109,9 @@ int chz_reset(chz_t* h);
 int chz_set_stream(chz_t* h, void* cuda_stream);
 
 /* Options (chz_set_option) */
-#define CHZ_OPT_RETAIN        1  /* 1 (default): chz_process keeps its output rows on the device for chz_pdws */
+#define CHZ_OPT_RETAIN        1  /* 1: chz_process also keeps its output rows on the device (a store that grows until chz_reset) so that
+                                    chz_pdws can run over them; 0 (default): rows only go to `out` -- frame-by-frame streaming in the
+                                    style of channelizer_example.m:50-56 then holds no memory beyond the FIR history */
 #define CHZ_OPT_CHUNK_ROWS    2  /* host path: rows per pipelined H2D/compute/D2H chunk (0 = auto) */
 #define CHZ_OPT_FORCE_PATH    3  /* kernel family: 0 auto (default), 1 fused kernel (M <= 560), 2 split FIR + row-FFT kernels,
                                     11 fused ring kernel (M = 1024: TMA-fed raw-sample ring, in-place FFT).  3-10 are the

@@ -107,10 +107,12 @@ class Channelizer:
     property names and defaults (12 taps per band, 80 dB, critically sampled).  `taps` overrides the
     designed prototype (length must be a multiple of M).  Stateful like the System object: FIR
     history carries across calls (channelizer_example.m:50-56) until reset().
+    retain=True additionally keeps every output row on the GPU (CHZ_OPT_RETAIN) so that pdws() can run
+    over everything processed since reset(); the default keeps nothing, as a streaming caller expects.
     """
 
     def __init__(self, NumFrequencyBands=8, NumTapsPerBand=12, StopbandAttenuation=80.0, OversamplingRatio=1,
-                 taps=None):
+                 taps=None, retain=False):
         self.NumFrequencyBands = int(NumFrequencyBands)
         self.OversamplingRatio = int(OversamplingRatio)
         if taps is None:
@@ -122,6 +124,14 @@ class Channelizer:
         check(lib().chz_create(self.NumFrequencyBands, taps.ctypes.data_as(C.c_void_p), len(taps),
                                self.OversamplingRatio, C.byref(self._h)), "chz_create")
         self._taps = taps
+        self._retain = False
+        if retain:
+            self.retain(True)
+
+    def retain(self, on=True):
+        """Keep (or stop keeping) the output rows of later calls on the GPU for pdws()."""
+        self.set_option(_lib.CHZ_OPT_RETAIN, 1 if on else 0)
+        self._retain = bool(on)
 
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self):
@@ -228,8 +238,11 @@ class Channelizer:
 
     def pdws(self, fs, fc=0.0, sampleStartTime=0.0, SNR_THRESHOLD=15.0, sat_level=0.9999,
              reproduce_phase_bug=False, TRAILING_EDGE_THRESHOLD=None):
-        """PDWs over everything processed since reset (create_pdws_channelized.m:60-136).
+        """PDWs over everything processed since reset (create_pdws_channelized.m:60-136); the handle must
+        have been retaining its rows (retain=True / retain()).
         -> (list of Pdw records in the reference's order, noise floor per natural channel)."""
+        if not self._retain:
+            raise ChannelizerError(_lib.CHZ_ESTATE, "pdws() needs Channelizer(..., retain=True)")
         prm = self._params(fs, fc, sampleStartTime, SNR_THRESHOLD, sat_level, reproduce_phase_bug, TRAILING_EDGE_THRESHOLD)
         return self._pdw_call(lib().chz_pdws, prm)
 
@@ -257,16 +270,17 @@ def create_pdws_channelized(recordings, M=None, NumTapsPerBand=12, SNR_THRESHOLD
                             reproduce_phase_bug=False, taps=None):
     """The reference script as a function: for each recording (path or IqRecording) build a fresh
     channelizer with M = fs*1e-6 bands unless given (:31-33), channelize, extract PDWs and
-    concatenate (:16-20,124-128).  M must be a power of two in [8, 4096] in this build.
+    concatenate (:16-20,124-128).  Any M in [1, 4096] (tuned kernels for powers of two, 56 and 560).
+    reproduce_phase_bug=True gives the frequencies the script as written emits (its :114 reads column 1's phase
+    for every bin); the default is the intended per-bin phase.
     Returns dict(toa, freq, pw, snr, sat, amp, channel) of numpy arrays."""
     out = {k: [] for k in ("toa", "freq", "pw", "snr", "sat", "amp", "channel")}
     for rec in recordings:
         if not isinstance(rec, IqRecording):
             rec = read_iq(rec)
         m = int(M) if M else int(round(rec.fs * 1e-6))            # :31
-        ch = Channelizer(m, NumTapsPerBand=NumTapsPerBand, taps=taps)   # :33
+        ch = Channelizer(m, NumTapsPerBand=NumTapsPerBand, taps=taps, retain=True)   # :33
         try:
-            ch.set_option(_lib.CHZ_OPT_RETAIN, 1)
             n = C.c_uint64(0)
             iq = np.ascontiguousarray(rec.iq)
             check(lib().chz_process(ch.handle, iq.ctypes.data_as(C.c_void_p), iq.shape[0], rec.bitWidth,
@@ -291,7 +305,7 @@ def create_pdws(recordings, SNR_THRESHOLD=18.0, TRAILING_EDGE_THRESHOLD=3.0):
     for rec in recordings:
         if not isinstance(rec, IqRecording):
             rec = read_iq(rec)
-        ch = Channelizer(1, taps=np.ones(1, dtype=np.float32))
+        ch = Channelizer(1, taps=np.ones(1, dtype=np.float32), retain=True)
         try:
             n = C.c_uint64(0)
             iq = np.ascontiguousarray(rec.iq)
@@ -348,7 +362,7 @@ def predict_event(recordings, SNR_THRESHOLD=20.0, min_peak=0.9):
         if not peak2 > (min_peak * full) ** 2:                             # :52  max(abs(iq)) > 0.9
             out["pdws_per_file"].append(0)
             continue
-        ch = Channelizer(1, taps=np.ones(1, dtype=np.float32))
+        ch = Channelizer(1, taps=np.ones(1, dtype=np.float32), retain=True)
         try:
             n = C.c_uint64(0)
             check(lib().chz_process(ch.handle, iq.ctypes.data_as(C.c_void_p), iq.shape[0], rec.bitWidth,

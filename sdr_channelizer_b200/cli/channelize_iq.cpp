@@ -37,6 +37,17 @@ namespace {
 struct Options {
   uint32_t channels = 0, tapsPerBand = 12, oversample = 1;
   double snrThresholdDb = 15.0;
+  bool bugCompat = false;   // reproduce create_pdws_channelized.m:114 (phase of column 1 for every bin)
+};
+
+// Closes the recording and frees the pinned output buffer on every exit path of processOne.
+struct FileGuard {
+  chz_iq_t* file = nullptr;
+  chz_cf32* out = nullptr;
+  ~FileGuard() {
+    if (out) chz_free_host(out);
+    if (file) chz_close_iq(file);
+  }
 };
 
 // One channelizer handle is kept across files while the geometry stays the same (chz_reset = a fresh
@@ -47,12 +58,16 @@ struct Engine {
   ~Engine() { if (chan) chz_destroy(chan); }
 };
 
-// 0 = done, > 0 = failure line, -1 = the file is not complete yet (watch mode retries it)
-int processOne(Engine& eng, const Options& opt, const std::string& path, const std::string& prefix) {
-  chz_iq_t* file = nullptr;
+// 0 = done, > 0 = failure line, -1 = the file is not complete yet (watch mode retries it; `why` says what is wrong)
+int processOne(Engine& eng, const Options& opt, const std::string& path, const std::string& prefix, int* why = nullptr) {
+  FileGuard guard;
+  chz_iq_t*& file = guard.file;
   chz_iq_info_t info;
   const int rc = chz_open_iq(path.c_str(), &file, &info);
-  if (rc == CHZ_ESIZE || rc == CHZ_EIO) return -1;     // header or payload still being written
+  if (rc == CHZ_ESIZE || rc == CHZ_EIO) {              // header or payload still being written
+    if (why) *why = rc;
+    return -1;
+  }
   CHECK(rc);
   std::cout << path << ": file format " << info.format << ", " << info.num_samples << " samples, " << info.bit_width
             << " bits, fs " << info.fs_sps << " sps, fc " << info.fc_hz << " Hz, board '" << info.board_name << "'"
@@ -65,6 +80,7 @@ int processOne(Engine& eng, const Options& opt, const std::string& path, const s
     std::vector<float> taps((size_t)channels * opt.tapsPerBand);
     CHECK(chz_design_prototype(channels, opt.tapsPerBand, 80.0, taps.data()));
     CHECK(chz_create(channels, taps.data(), (uint32_t)taps.size(), opt.oversample, &eng.chan));
+    CHECK(chz_set_option(eng.chan, CHZ_OPT_RETAIN, 1));   // chz_pdws below runs over the rows kept on the GPU
     eng.channels = channels;
   } else {
     CHECK(chz_reset(eng.chan));
@@ -72,7 +88,7 @@ int processOne(Engine& eng, const Options& opt, const std::string& path, const s
   chz_t* chan = eng.chan;
 
   const uint64_t rows = chz_rows_for(chan, info.num_samples);
-  chz_cf32* out = nullptr;
+  chz_cf32*& out = guard.out;
   if (!prefix.empty()) {
     out = (chz_cf32*)chz_alloc_host(rows * channels * sizeof(chz_cf32));
     if (!out) { std::cerr << "pinned allocation failed" << std::endl; return __LINE__; }
@@ -90,6 +106,7 @@ int processOne(Engine& eng, const Options& opt, const std::string& path, const s
   prm.fs_sps = (double)info.fs_sps;
   prm.t0 = info.sample_start_time;
   prm.use_trailing_threshold = 0;
+  prm.reproduce_phase_bug = opt.bugCompat ? 1 : 0;
   uint64_t npdw = 0;
   const int status = chz_pdws(chan, &prm, nullptr, 0, &npdw);
   if (status != 0 && status != CHZ_ECAPACITY) CHECK(status);
@@ -121,8 +138,6 @@ int processOne(Engine& eng, const Options& opt, const std::string& path, const s
     if (std::rename(tmpName.c_str(), pdwName.c_str()) != 0) return __LINE__;
     std::cout << "Wrote " << chanName << " and " << pdwName << std::endl;
   }
-  if (out) chz_free_host(out);
-  chz_close_iq(file);
   return 0;
 }
 
@@ -156,7 +171,8 @@ int main(int argc, char** argv) {
     std::cerr << "Usage: " << argv[0]
               << " <recording.iq | directory to watch> <channels (0 = sampleRate*1e-6)> <tapsPerBand> <oversample 1|2>"
                  " [snrThresholdDb=15] [outputPrefix | output directory] [idleSec=10 (watch mode: exit after this"
-                 " long without a new file, or when a file named 'stop' appears)]"
+                 " long without a new file, or when a file named 'stop' appears)] [bugCompat=0 (1: pdw freq as"
+                 " create_pdws_channelized.m:114 computes it, from column 1's phase)]"
               << std::endl;
     return __LINE__;
   }
@@ -168,13 +184,27 @@ int main(int argc, char** argv) {
   opt.snrThresholdDb = argc > 5 ? std::atof(argv[5]) : 15.0;
   const std::string prefix = argc > 6 ? argv[6] : "";
   const double idleSec = argc > 7 ? std::atof(argv[7]) : 10.0;
+  opt.bugCompat = argc > 8 && std::atoi(argv[8]) != 0;
   Engine eng;
 
-  if (!isDirectory(input)) return processOne(eng, opt, input, prefix);
+  if (!isDirectory(input)) {
+    int why = 0;
+    const int rc = processOne(eng, opt, input, prefix, &why);
+    if (rc == -1) {   // a truncated or unreadable recording is an error outside watch mode
+      std::cerr << input << ": " << chz_strerror(why) << std::endl;
+      return __LINE__;
+    }
+    return rc;
+  }
 
   // watch mode: dwell files appear one by one while the recorder runs
   const std::string outDir = prefix.empty() ? input : prefix;
   std::set<std::string> done;
+  // an incomplete file is waited for only while it keeps growing: a file that failed to open twice in a row
+  // with the same size, at least a second apart, is reported and skipped so that it cannot block later dwells
+  std::string stuckName;
+  long long stuckSize = -1;
+  auto stuckSince = std::chrono::steady_clock::now();
   auto lastWork = std::chrono::steady_clock::now();
   uint64_t processed = 0;
   for (;;) {
@@ -182,8 +212,19 @@ int main(int argc, char** argv) {
     for (const std::string& name : listIq(input)) {
       if (done.count(name)) continue;
       const std::string stem = name.substr(0, name.size() - 3);
-      const int rc = processOne(eng, opt, input + "/" + name, outDir + "/" + stem);
-      if (rc == -1) break;                       // still being written: files are handled in time order, so wait for it
+      int why = 0;
+      const int rc = processOne(eng, opt, input + "/" + name, outDir + "/" + stem, &why);
+      if (rc == -1) {                            // still being written: files are handled in time order, so wait for it
+        struct stat st;
+        const long long size = stat((input + "/" + name).c_str(), &st) == 0 ? (long long)st.st_size : -1;
+        const auto now = std::chrono::steady_clock::now();
+        if (name != stuckName || size != stuckSize) { stuckName = name; stuckSize = size; stuckSince = now; break; }
+        if (std::chrono::duration<double>(now - stuckSince).count() < 1.0) break;
+        std::cerr << input << "/" << name << ": skipped, " << chz_strerror(why) << " and the file stopped growing" << std::endl;
+        done.insert(name);
+        stuckName.clear();
+        continue;
+      }
       if (rc != 0) return rc;
       done.insert(name);
       processed++;

@@ -267,11 +267,11 @@ static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, 
       if (rc == 1) return CHZ_EINVAL;
       if (rc) return rc;
     } else {
-      // split path: FIR rows -> the output buffer itself, then the row FFT over it IN PLACE.  The
-      // recording is walked in row chunks small enough that a chunk's FIR output is still in the 126 MB
-      // L2 when the FFT kernel reads it and overwrites it with the final rows: the intermediate then
-      // never travels to DRAM, which keeps traffic near the fused kernel's 4 + 8 B per sample instead
-      // of 4 + 8 + 8 + 8.
+      // split path: FIR rows -> the output buffer itself, then the row FFT over it IN PLACE: 4 + 8 + 8 + 8 B per
+      // sample through DRAM.  By default the whole call is one FIR launch and one FFT launch.  CHZ_SPLIT_CHUNK_MB
+      // walks the rows in chunks small enough for the FIR output to stay in the 126 MB L2 until the FFT reads it;
+      // measured slower on B200 (the small launches lose more to ramps and tails than the L2 hits give back,
+      // DESIGN.md section 4), so it stays a tuning aid.
       long long chunk_rows = (long long)(h->split_chunk_bytes / ((uint64_t)h->M * sizeof(float2)));
       chunk_rows &= ~1LL;                       // even: row pairs stay aligned to global parity
       if (chunk_rows < 2) chunk_rows = 2;
@@ -349,7 +349,16 @@ static int ensure_store(::chz* h, uint64_t rows_needed) {
   uint64_t cap = h->store_cap * 2;
   if (cap < rows_needed) cap = rows_needed;
   float2* nb = nullptr;
-  CHZ_CUDA(cudaMalloc(&nb, cap * h->M * sizeof(float2)));
+  {
+    cudaError_t e = cudaMalloc(&nb, cap * h->M * sizeof(float2));
+    if (e == cudaErrorMemoryAllocation && cap > rows_needed) {   // doubling does not fit: take exactly what is needed
+      cudaGetLastError();
+      cap = rows_needed;
+      e = cudaMalloc(&nb, cap * h->M * sizeof(float2));
+    }
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return CHZ_ENOMEM; }
+    CHZ_CUDA(e);
+  }
   if (h->store_rows) {
     CHZ_CUDA(cudaMemcpyAsync(nb, h->d_store, h->store_rows * h->M * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
     CHZ_CUDA(cudaStreamSynchronize(h->stream));
@@ -364,6 +373,7 @@ static int check_stream_args(::chz* h, uint64_t nsamp, uint32_t bw) {
   if (bw == 0 || bw > 16) return CHZ_EBITWIDTH;
   if (h->consumed + nsamp > (1ULL << 62)) return CHZ_EINVAL;
   if (h->bit_width && h->bit_width != bw) return CHZ_ESTATE;   // one sample format per stream; chz_reset to change
+  if (h->poisoned) return CHZ_ESTATE;                           // an earlier call failed half way: chz_reset first
   return CHZ_OK;
 }
 
@@ -563,6 +573,7 @@ int chz_reset(chz_t* h) {
   h->consumed = 0; h->rows_done = 0; h->bit_width = 0;
   h->hist_base = 0; h->hist_len = 0;
   h->store_rows = 0;
+  h->poisoned = false;
   h->pdws.clear(); h->noise_floor.clear();
   return CHZ_OK;
 }
@@ -682,39 +693,52 @@ int chz_process(chz_t* h, const void* iq, uint64_t nsamp, uint32_t bit_width, ch
   cudaStream_t sc = h->stream;
   uint64_t done = 0, rows_out = 0;
   int c = 0;
-  // make the side streams wait for whatever is already queued on the compute stream
-  CHZ_CUDA(cudaEventRecord(h->ev_comp[0], sc));
-  CHZ_CUDA(cudaEventRecord(h->ev_comp[1], sc));
-  CHZ_CUDA(cudaEventRecord(h->ev_d2h[0], h->s_d2h));
-  CHZ_CUDA(cudaEventRecord(h->ev_d2h[1], h->s_d2h));
-  while (done < nsamp) {
-    const int b = c & 1;
-    const uint64_t n = (nsamp - done) < csamp ? (nsamp - done) : csamp;
-    // H2D of chunk c may start once the kernel that last read d_in[b] (chunk c-2) is done
-    CHZ_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));
-    if (n) CHZ_CUDA(cudaMemcpyAsync(h->d_in[b], (const char*)iq + done * bps, n * bps, cudaMemcpyHostToDevice, h->s_h2d));
-    CHZ_CUDA(cudaEventRecord(h->ev_h2d[b], h->s_h2d));
-    CHZ_CUDA(cudaStreamWaitEvent(sc, h->ev_h2d[b], 0));
-    float2* dst;
-    if (h->retain) dst = h->d_store + h->store_rows * M;
-    else { dst = h->d_out[b]; CHZ_CUDA(cudaStreamWaitEvent(sc, h->ev_d2h[b], 0)); }
-    uint64_t r = 0;
-    rc = run_chunk(h, h->d_in[b], n, bit_width, dst, &r, sc);
-    if (rc) return rc;
-    CHZ_CUDA(cudaEventRecord(h->ev_comp[b], sc));
-    if (h->retain) h->store_rows += r;
-    if (out && r) {
-      CHZ_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
-      CHZ_CUDA(cudaMemcpyAsync(out + rows_out * M, dst, r * M * sizeof(float2), cudaMemcpyDeviceToHost, h->s_d2h));
-      CHZ_CUDA(cudaEventRecord(h->ev_d2h[b], h->s_d2h));
+  // A failure in the middle of the pipeline leaves copies in flight that reference the caller's buffers and a
+  // stream state that has advanced for some chunks only: drain the three streams before returning and mark the
+  // handle so that nothing but chz_reset is accepted afterwards.
+  auto pipeline = [&]() -> int {
+    // make the side streams wait for whatever is already queued on the compute stream
+    CHZ_CUDA(cudaEventRecord(h->ev_comp[0], sc));
+    CHZ_CUDA(cudaEventRecord(h->ev_comp[1], sc));
+    CHZ_CUDA(cudaEventRecord(h->ev_d2h[0], h->s_d2h));
+    CHZ_CUDA(cudaEventRecord(h->ev_d2h[1], h->s_d2h));
+    while (done < nsamp) {
+      const int b = c & 1;
+      const uint64_t n = (nsamp - done) < csamp ? (nsamp - done) : csamp;
+      // H2D of chunk c may start once the kernel that last read d_in[b] (chunk c-2) is done
+      CHZ_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));
+      if (n) CHZ_CUDA(cudaMemcpyAsync(h->d_in[b], (const char*)iq + done * bps, n * bps, cudaMemcpyHostToDevice, h->s_h2d));
+      CHZ_CUDA(cudaEventRecord(h->ev_h2d[b], h->s_h2d));
+      CHZ_CUDA(cudaStreamWaitEvent(sc, h->ev_h2d[b], 0));
+      float2* dst;
+      if (h->retain) dst = h->d_store + h->store_rows * M;
+      else { dst = h->d_out[b]; CHZ_CUDA(cudaStreamWaitEvent(sc, h->ev_d2h[b], 0)); }
+      uint64_t r = 0;
+      const int rcc = run_chunk(h, h->d_in[b], n, bit_width, dst, &r, sc);
+      if (rcc) return rcc;
+      CHZ_CUDA(cudaEventRecord(h->ev_comp[b], sc));
+      if (h->retain) h->store_rows += r;
+      if (out && r) {
+        CHZ_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
+        CHZ_CUDA(cudaMemcpyAsync(out + rows_out * M, dst, r * M * sizeof(float2), cudaMemcpyDeviceToHost, h->s_d2h));
+        CHZ_CUDA(cudaEventRecord(h->ev_d2h[b], h->s_d2h));
+      }
+      rows_out += r;
+      done += n;
+      c++;
     }
-    rows_out += r;
-    done += n;
-    c++;
+    CHZ_CUDA(cudaStreamSynchronize(h->s_h2d));
+    CHZ_CUDA(cudaStreamSynchronize(sc));
+    CHZ_CUDA(cudaStreamSynchronize(h->s_d2h));
+    return CHZ_OK;
+  };
+  rc = pipeline();
+  if (rc) {
+    cudaStreamSynchronize(h->s_h2d); cudaStreamSynchronize(sc); cudaStreamSynchronize(h->s_d2h);
+    h->poisoned = true;
+    if (nrows) *nrows = 0;
+    return rc;
   }
-  CHZ_CUDA(cudaStreamSynchronize(h->s_h2d));
-  CHZ_CUDA(cudaStreamSynchronize(sc));
-  CHZ_CUDA(cudaStreamSynchronize(h->s_d2h));
   if (nrows) *nrows = rows_out;
   return CHZ_OK;
 }

@@ -65,7 +65,8 @@ struct chz {
   uint64_t hist_base = 0, hist_len = 0, hist_cap = 0;   // samples
 
   // retained channel output (for chz_pdws)
-  bool retain = true;
+  bool retain = false;                  // CHZ_OPT_RETAIN: off unless the caller wants chz_pdws over the processed rows
+  bool poisoned = false;                // a chz_process call failed mid-pipeline: only chz_reset is valid
   float2* d_store = nullptr;
   uint64_t store_rows = 0, store_cap = 0;
 

@@ -332,7 +332,8 @@ static __global__ void __launch_bounds__(256) k_fft_rows_mixed(const float2* u, 
 // Split path, kernel B (also K3 on its own): M-point FFT of rows in global memory.
 // One block transforms ROWS rows at a time.  Dynamic smem: 2 * ROWS * RowStride<M> float2 + M float2.
 template <int M, int ROWS, int NT>
-__global__ void __launch_bounds__(NT) k_fft_rows(const float2* __restrict__ u, float2* __restrict__ y,
+__global__ void __launch_bounds__(NT) k_fft_rows(const float2* u, float2* y,   // launched in place (u == y): no __restrict__
+                                                
                                                  const float2* __restrict__ tw_g, long long nrows) {
   extern __shared__ float2 smem[];
   constexpr int S = RowStride<M>::value;

@@ -110,7 +110,7 @@ def test_end_to_end_pulsed_recording(orc, M, P, seed, tmp_path):
     pkg.write_iq(path, iq, fs=fs, fc=2.4e9, bitWidth=bw, sampleStartTime=1.7e9, fileFormat=1 if M <= 64 else 3)
     taps = pkg.design_prototype(M, P)
     rec = pkg.read_iq(path)
-    ch = pkg.Channelizer(M, taps=taps)
+    ch = pkg.Channelizer(M, taps=taps, retain=True)
     y = ch(rec.iq, rec.bitWidth)
     recs, nf = ch.pdws(rec.fs, rec.fc, rec.sampleStartTime)
     ch.close()
@@ -318,7 +318,7 @@ def _cli():
 
 def _expected(path, M, P):
     rec = pkg.read_iq(path)
-    ch = pkg.Channelizer(M, taps=pkg.design_prototype(M, P))
+    ch = pkg.Channelizer(M, taps=pkg.design_prototype(M, P), retain=True)
     y = ch(rec.iq, rec.bitWidth).copy()
     recs, _ = ch.pdws(rec.fs, rec.fc, rec.sampleStartTime)
     ch.close()
