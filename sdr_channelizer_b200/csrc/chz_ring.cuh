@@ -23,12 +23,13 @@ constexpr int kM = 1024;        // channels = branches per CTA
 constexpr int kNT = 512;        // threads: two adjacent branches each
 constexpr int kR = 8;           // output rows per tile = frames per ring slot
 constexpr int kSlots = 3;       // ring = 3 slots of 8 frames: rows a0-16 .. a0+7 of the step at a0
-constexpr int kTileStride = kM + 2 * (kM / 128);   // float2 per tile row: 2 pad elements per 128 (see pass 2)
+constexpr int kTileStride = kM + 2 * (kM / 128) - 2;   // float2 per tile row: 2 pad elements after each 128-block but the last (see pass 2)
 
 struct RingParams {
   long long a_lo;       // first frame whose rows this launch produces (row m = os*a + phase)
   long long nsteps;     // steps of 8 frames over all CTAs
   const float2* twn;    // e^{+j 2 pi i / M}, i < M
+  int dbg;              // timing experiments only (CHZ_RING_DBG), bit flags: 1 skip the FFT passes, 2 skip the FIR, 4 skip the ring loads; results are garbage
 };
 
 template <bool IN16> struct Smem {
@@ -36,7 +37,7 @@ template <bool IN16> struct Smem {
   static constexpr int ROWB = kM * (int)sizeof(raw_t);            // bytes per frame
   static constexpr int SLOTB = kR * ROWB;                         // bytes per ring slot
   static constexpr int RING = kSlots * SLOTB;
-  static constexpr int TILE = kR * kTileStride * (int)sizeof(float2);
+  static constexpr int TILE = 2 * kR * kTileStride * (int)sizeof(float2);   // two tile buffers: the FIR of a phase writes one while the FFT of the previous phase still reads the other
   static constexpr int OFF_TILE = RING;
   static constexpr int OFF_H0 = OFF_TILE + TILE;                  // taps of branch 0 (32 floats)
   static constexpr int OFF_TW1 = OFF_H0 + 32 * (int)sizeof(float);   // pass-1 twiddles W_128^{j1 k}: [7][16] float2
@@ -68,19 +69,16 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 }
 
 // Unpack policies for one raw word (int16 I | int16 Q << 16, or int8 pair) -> integer-valued float2.
-//   0: two I2F (conversion pipe)   1: I2F for I, shift + I2FP (ALU pipe) for Q   2: sign-extend + I2FP for both
+//   0: two I2F.S16 (conversion pipe behind the MIO queue)
+//   1: I2F.S16 for I, arithmetic shift + I2FP.F32.S32 (ALU pipe) for Q  -- default, 4 % faster than 0 on B200
+// Also measured and dropped (profiles/r02b_ring_unpack_ab.jsonl): PRMT sign extension + I2FP for both halves, and the
+// magic-number form ((x ^ 0x8000) | 0x4B400000, one packed FADD2): both within 1 % of policy 1 -- the FIR is bound by
+// register-file bandwidth of its FFMA2s (2.8 cycles each with three distinct operands, tools/ubench/pipes.cu), not by
+// the conversions.
 template <bool IN16, int UNPACK>
 __device__ __forceinline__ float2 unpack(uint32_t raw) {
-  if (!IN16) {
-    if (UNPACK == 0) return unpack_raw<false>(raw);
-    const int q = ((int)(raw << 16)) >> 24, i = ((int)(raw << 24)) >> 24;
-    return make_float2(__int2float_rn(i), __int2float_rn(q));
-  }
-  if (UNPACK == 0) return unpack_raw<true>(raw);
-  const int q = ((int)raw) >> 16;
-  if (UNPACK == 1) return make_float2((float)(short)(raw & 0xffffu), __int2float_rn(q));
-  const int i = ((int)(raw << 16)) >> 16;
-  return make_float2(__int2float_rn(i), __int2float_rn(q));
+  if (!IN16 || UNPACK == 0) return unpack_raw<IN16>(raw);
+  return make_float2((float)(short)(raw & 0xffffu), __int2float_rn(((int)raw) >> 16));
 }
 
 // tile element index of channel position pos: two pad elements per 128 so that the eight lanes of a
@@ -94,7 +92,7 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
   constexpr int M = kM, ROWB = SM::ROWB, SLOTB = SM::SLOTB, TS = kTileStride;
   constexpr int J0 = 16 - P;                      // first ring row (relative to a0-16) a delta = 0 thread reads
   extern __shared__ __align__(128) unsigned char smem[];
-  float2* tile = (float2*)(smem + SM::OFF_TILE);
+  float2* tiles = (float2*)(smem + SM::OFF_TILE);
   float* h0s = (float*)(smem + SM::OFF_H0);
   float2* tw1s = (float2*)(smem + SM::OFF_TW1);
   const unsigned ring_s = smem_u32(smem), bar = smem_u32(smem + SM::OFF_BAR);
@@ -133,6 +131,7 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
   // checks (history buffer, zeros before the stream start and past the data) and the caller synchronises.
   auto load_slot = [&](long long a, int s) -> bool {
     const long long lo = a * M, hi = lo + (long long)kR * M;
+    if (rp.dbg & 4) return false;
     if (aligned && lo >= prm.in_base && hi <= in_end) {
       if (t == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -156,15 +155,22 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
   __syncthreads();
   pending = load_slot(a_start, 2);
 
+  __syncthreads();                                 // ring writes of a slow-path warm-up are visible
+
+  // Per phase: FIR -> tile[buf] | CTA barrier | pass 0 | pass 1 | pass 2 + global stores -> straight into the next
+  // phase's FIR, which writes the OTHER tile buffer.  Rows are independent in the FFT, so its passes are separated by
+  // named barriers of the four warps that own a pair of rows only; one CTA-wide barrier remains per eight rows, and a
+  // warp that is done with its rows starts filtering while others still stream theirs out.
   int s_old = 0;                                   // slot of frames a0-16 .. a0-9
+  int buf = 0;
   for (long long k = k0; k < k1; k++) {
     const long long a0 = rp.a_lo + k * kR;
     const int s_mid = s_old == 2 ? 0 : s_old + 1, s_new = s_mid == 2 ? 0 : s_mid + 1;
-    __syncthreads();                               // last step's pass 2 has read the tile; slow-path ring writes are visible
     if (pending) { mbar_wait(bar, parity); parity ^= 1; }
     const unsigned sb0 = ring_s + s_old * SLOTB, sb1 = ring_s + s_mid * SLOTB, sb2 = ring_s + s_new * SLOTB;
 
-    for (int ph = 0; ph < os; ph++) {
+    for (int ph = 0; ph < os; ph++, buf ^= 1) {
+      float2* tile = tiles + buf * (kR * TS);
       // ---- FIR: 8 rows x 2 branches per thread ----
       // Row m = os*a + ph, branch p reads x[a M + ph D - q M - p] = frame (a - q - 1 + delta), column cl:
       //   ph = 0: cl = M - p, delta = 0 (p >= 1);  ph = 1: p <= D: cl = D - p, delta = 1;  p > D: cl = M + D - p, delta = 0.
@@ -176,59 +182,64 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
       const unsigned r0b = sb0 + dcol, r1b = sb1 + dcol, r2b = sb2 + dcol;
       const unsigned e0 = lowhalf ? sb1 + cl * (unsigned)sizeof(raw_t) : sb0 + 7 * ROWB + cl * (unsigned)sizeof(raw_t);
       const unsigned e1 = lowhalf ? sb2 + cl * (unsigned)sizeof(raw_t) : sb1 + 7 * ROWB + cl * (unsigned)sizeof(raw_t);
-      float2 acc1[kR], acc2[kR];
-      #pragma unroll
-      for (int r = 0; r < kR; r++) { acc1[r] = make_float2(0.f, 0.f); acc2[r] = make_float2(0.f, 0.f); }
-      #pragma unroll
-      for (int ii = 0; ii < P + kR - 1; ii++) {
-        const int j = ii + J0;                       // ring row (before delta), compile time
-        const unsigned addr = (j & 7) == 7 ? (j < 8 ? e0 : e1) : ((j < 8 ? r0b : (j < 16 ? r1b : r2b)) + (j & 7) * ROWB);
-        uint32_t wa, wb;                             // columns cl (branch 2t+2) and cl+1 (branch 2t+1)
-        if (IN16) {
-          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wa), "=r"(wb) : "r"(addr));
-        } else {
-          uint32_t w;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
-          wa = w & 0xffffu; wb = w >> 16;
-        }
-        const float2 xa = unpack<IN16, UNPACK>(wa), xb = unpack<IN16, UNPACK>(wb);
+      if (!(rp.dbg & 2)) {
+        float2 acc1[kR], acc2[kR];
         #pragma unroll
-        for (int r = 0; r < kR; r++) {
-          const int q = r + P - 1 - ii;
-          if (q >= 0 && q < P) {
-            acc2[r] = __ffma2_rn(make_float2(h2[q], h2[q]), xa, acc2[r]);
-            acc1[r] = __ffma2_rn(make_float2(h1[q], h1[q]), xb, acc1[r]);
-          }
-        }
-      }
-      const int shift = ph ? D : 0;
-      const int pos1 = tpad((b1 - shift) & (M - 1)), pos2 = tpad((b2 - shift) & (M - 1));
-      #pragma unroll
-      for (int r = 0; r < kR; r++) { tile[r * TS + pos1] = acc1[r]; tile[r * TS + pos2] = acc2[r]; }
-      if (t >= kNT - 32) {
-        // branch 0: u_0[m] = sum_q h[qM] x[a M + ph D - q M] = frame (a - q), column ph*D: rows 16 + r - q of the ring
-        __syncwarp();
-        const int r = t & 31;
-        if (r < kR) {
-          float2 acc = make_float2(0.f, 0.f);
-          const unsigned c0 = (unsigned)(ph ? D : 0) * sizeof(raw_t);
-          #pragma unroll
-          for (int q = P - 1; q >= 0; q--) {
-            const int i = 16 + r - q;                 // 1 .. 23
-            const unsigned sb = i < 8 ? sb0 : (i < 16 ? sb1 : sb2);
+        for (int r = 0; r < kR; r++) { acc1[r] = make_float2(0.f, 0.f); acc2[r] = make_float2(0.f, 0.f); }
+        #pragma unroll
+        for (int ii = 0; ii < P + kR - 1; ii++) {
+          const int j = ii + J0;                       // ring row (before delta), compile time
+          const unsigned addr = (j & 7) == 7 ? (j < 8 ? e0 : e1) : ((j < 8 ? r0b : (j < 16 ? r1b : r2b)) + (j & 7) * ROWB);
+          uint32_t wa, wb;                             // columns cl (branch 2t+2) and cl+1 (branch 2t+1)
+          if (IN16) {
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wa), "=r"(wb) : "r"(addr));
+          } else {
             uint32_t w;
-            if (IN16) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sb + (i & 7) * ROWB + c0));
-            else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w) : "r"(sb + (i & 7) * ROWB + c0));
-            acc = __ffma2_rn(make_float2(h0s[q], h0s[q]), unpack<IN16, UNPACK>(w), acc);
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
+            wa = w & 0xffffu; wb = w >> 16;
           }
-          tile[r * TS + tpad((0 - shift) & (M - 1))] = acc;
+          const float2 xa = unpack<IN16, UNPACK>(wa), xb = unpack<IN16, UNPACK>(wb);
+          #pragma unroll
+          for (int r = 0; r < kR; r++) {
+            const int q = r + P - 1 - ii;
+            if (q >= 0 && q < P) acc2[r] = __ffma2_rn(make_float2(h2[q], h2[q]), xa, acc2[r]);
+          }
+          #pragma unroll
+          for (int r = 0; r < kR; r++) {
+            const int q = r + P - 1 - ii;
+            if (q >= 0 && q < P) acc1[r] = __ffma2_rn(make_float2(h1[q], h1[q]), xb, acc1[r]);
+          }
+        }
+        const int shift = ph ? D : 0;
+        const int pos1 = tpad((b1 - shift) & (M - 1)), pos2 = tpad((b2 - shift) & (M - 1));
+        #pragma unroll
+        for (int r = 0; r < kR; r++) { tile[r * TS + pos1] = acc1[r]; tile[r * TS + pos2] = acc2[r]; }
+        if (t >= kNT - 32) {
+          // branch 0: u_0[m] = sum_q h[qM] x[a M + ph D - q M] = frame (a - q), column ph*D: rows 16 + r - q of the ring
+          __syncwarp();
+          const int r = t & 31;
+          if (r < kR) {
+            float2 acc = make_float2(0.f, 0.f);
+            const unsigned c0 = (unsigned)(ph ? D : 0) * sizeof(raw_t);
+            #pragma unroll
+            for (int q = P - 1; q >= 0; q--) {
+              const int i = 16 + r - q;                 // 1 .. 23
+              const unsigned sb = i < 8 ? sb0 : (i < 16 ? sb1 : sb2);
+              uint32_t w;
+              if (IN16) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sb + (i & 7) * ROWB + c0));
+              else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w) : "r"(sb + (i & 7) * ROWB + c0));
+              acc = __ffma2_rn(make_float2(h0s[q], h0s[q]), unpack<IN16, UNPACK>(w), acc);
+            }
+            tile[r * TS + tpad((0 - shift) & (M - 1))] = acc;
+          }
         }
       }
-      __syncthreads();
+      __syncthreads();                               // barrier A: the tile is complete, nobody reads the ring any more
       // the oldest slot is dead after the last phase's FIR: request the next step's frames into it now, the
       // copy lands while the FFT passes run
       if (ph == os - 1) pending = (k + 1 < k1) ? load_slot(a0 + kR, s_old) : false;
 
+      if (rp.dbg & 1) continue;
       // ---- FFT, decimation in frequency, in place: 8 (stride 128) x 8 (stride 16) x 16 (contiguous) ----
       {   // pass 0: z_{k0}[j] = W_M^{j k0} sum_q u[j + 128 q] W_8^{q k0}  ->  position 128 k0 + j
         const int j = t & 127, rr = t >> 7;
@@ -245,7 +256,8 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
           for (int q = 0; q < 8; q++) row[q * 130] = v[q];
         }
       }
-      __syncthreads();
+      // the rest of the FFT is local to a pair of rows: rows rr and rr + 4 belong to the four warps t >> 7
+      asm volatile("bar.sync %0, 128;" ::"r"((t >> 7) + 1) : "memory");
       {   // pass 1 inside block k0: w_{k1}[j1] = W_128^{j1 k1} sum_q z[j1 + 16 q] W_8^{q k1}  ->  position 128 k0 + 16 k1 + j1
         const int j1 = t & 15, kb = (t >> 4) & 7, rr = t >> 7;
         #pragma unroll
@@ -261,9 +273,10 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
           for (int q = 0; q < 8; q++) row[q * 16] = v[q];
         }
       }
-      __syncthreads();
+      asm volatile("bar.sync %0, 128;" ::"r"((t >> 7) + 1) : "memory");
+      const int row_i = (t >> 7) + 4 * ((t >> 6) & 1), b = t & 63;
       {   // pass 2: y[k0 + 8 k1 + 64 k2] = sum_{j1} w[j1] W_16^{j1 k2}; lanes run over (k0, k1): 32 consecutive channels per store
-        const int row_i = t >> 6, b = t & 63, kb = b & 7, kc = b >> 3;
+        const int kb = b & 7, kc = b >> 3;
         const float4* src = (const float4*)(tile + row_i * TS + kb * 130 + kc * 16);
         float2 v[16];
         #pragma unroll
@@ -279,7 +292,6 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
           for (int q = 0; q < 16; q++) g[q * 64] = v[q];
         }
       }
-      if (ph + 1 < os) __syncthreads();             // the next phase's FIR overwrites the tile
     }
     s_old = s_mid;
   }
