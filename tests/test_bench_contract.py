@@ -33,7 +33,7 @@ def test_reference_arm_line():
 
 @pytest.mark.gpu
 def test_b200_arm_line():
-    d = _run("--steps", "3", "--warmup", "3", "--seconds", "0.5")
+    d = _run("--steps", "3", "--warmup", "3", "--seconds", "0.5", "--no-others")   # the other configs are the driver run's business
     assert BASE_KEYS <= set(d) and d.get("impl") != "reference"
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["scaling"] == "weak" and d["n_gpus"] == 1
     r = d["roofline"]
@@ -43,3 +43,7 @@ def test_b200_arm_line():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 2 * e["h2d_bytes_per_step"]
     assert e["value"] < d["value"]                       # host copies are inside the timed region
     assert d["gpu_launches"] == d["steps"] and "sm_mhz" in d["clocks"]
+    assert e["matches_device_path"] is True and 0 < e["frac_of_copy_ceiling"] < 1.5
+    p = d["parity"]["configs[1]"]
+    assert p["ok"] and p["rows_checked"] >= 32 and p["max_rel_rms"] <= 1e-5
+    assert d["e2e_pdw"]["value"] > 0 and 0 < r["frac_sustained"] < 1.2
