@@ -118,6 +118,9 @@ int chz_set_stream(chz_t* h, void* cuda_stream);
                                     round-1 large-M / warp-specialisation experiments, present only in a `make EXPERIMENTS=1`
                                     build.  A path that is not built, or has no kernel for the handle's
                                     (M, taps), is refused with CHZ_EINVAL. */
+#define CHZ_OPT_PDW_EVENT_PATH 4  /* 1: chz_pdws* always uses the edge-event path (events to the host, radix sort, pairing, second launch
+                                    for the statistics) that the single-synchronisation extractor falls back to when a sample sits
+                                    exactly on a representable threshold; 0 (default): automatic.  For A/B runs and tests. */
 int chz_set_option(chz_t* h, int opt, int64_t value);
 
 uint32_t chz_num_channels(const chz_t* h);

@@ -5,7 +5,7 @@ matlab/create_pdws_channelized.m on recordings in the cpp/IqPacket.h format).  T
 ABI in include/channelizer.h (libchannelizer.so); this package is its Python host-side mirror.
 There is no CPU path: without the built library and a B200 the compute calls raise.
 """
-from ._lib import (CHZ_OPT_CHUNK_ROWS, CHZ_OPT_FORCE_PATH, CHZ_OPT_RETAIN, LIB_PATH, ChannelizerError, IqInfo, Pdw,
+from ._lib import (CHZ_OPT_CHUNK_ROWS, CHZ_OPT_FORCE_PATH, CHZ_OPT_PDW_EVENT_PATH, CHZ_OPT_RETAIN, LIB_PATH, ChannelizerError, IqInfo, Pdw,
                    PdwParams, lib)
 from .channelizer import (Channelizer, IqRecording, create_pdws, create_pdws_channelized, design_prototype, event_peak_time,
                           next_event_time, predict_event, read_iq, spectrogram_my_iq, stft, unpack_ptr, write_iq)

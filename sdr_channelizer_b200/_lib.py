@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("CHZ_LIB_PATH") or os.path.join(_HERE, "libchannelizer
 CHZ_OK = 0
 CHZ_EINVAL, CHZ_EIO, CHZ_EFORMAT, CHZ_EBITWIDTH, CHZ_ESIZE = -1, -2, -3, -4, -5
 CHZ_ENOMEM, CHZ_ECUDA, CHZ_ENODEVICE, CHZ_ECAPACITY, CHZ_ESTATE = -6, -7, -8, -9, -10
-CHZ_OPT_RETAIN, CHZ_OPT_CHUNK_ROWS, CHZ_OPT_FORCE_PATH = 1, 2, 3
+CHZ_OPT_RETAIN, CHZ_OPT_CHUNK_ROWS, CHZ_OPT_FORCE_PATH, CHZ_OPT_PDW_EVENT_PATH = 1, 2, 3, 4
 
 # every symbol include/channelizer.h declares (tests check the library exports them all)
 EXPORTS = [

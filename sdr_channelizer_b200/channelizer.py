@@ -97,6 +97,38 @@ def design_prototype(M, NumTapsPerBand=12, StopbandAttenuation=80.0) -> np.ndarr
     return taps
 
 
+class PdwTable:
+    """Read-only sequence of Pdw records over the ctypes array the library filled: len(), indexing, iteration
+    and comparison with a list, without building one Python object per record up front (at a few hundred
+    records per 100 ms file that conversion cost more than the GPU extraction itself)."""
+
+    def __init__(self, arr, n):
+        self._arr, self._n = arr, int(n)
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._arr[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        return self._arr[i]
+
+    def __iter__(self):
+        return (self._arr[i] for i in range(self._n))
+
+    def __eq__(self, other):
+        return len(other) == self._n and all(a is b or bytes(a) == bytes(b) for a, b in zip(self, other))
+
+    def to_numpy(self):
+        """Structured numpy view of the records (field names of chz_pdw_t)."""
+        dt = np.dtype([(name, ctype) for name, ctype in Pdw._fields_])
+        return np.frombuffer(self._arr, dtype=dt, count=self._n) if self._n else np.empty(0, dtype=dt)
+
+
 # ------------------------------------------------------------------------------------------------
 # R4-R7  dsp.Channelizer mirror
 # ------------------------------------------------------------------------------------------------
@@ -234,7 +266,7 @@ class Channelizer:
             check(lib().chz_pdws_fetch(self._h, C.cast(arr, C.c_void_p), cnt, C.byref(n)), "chz_pdws_fetch")
         nf = np.empty(self.NumFrequencyBands, dtype=np.float64)
         check(lib().chz_pdw_noise_floor(self._h, nf.ctypes.data_as(C.c_void_p), len(nf)), "chz_pdw_noise_floor")
-        return [arr[i] for i in range(cnt)], nf
+        return PdwTable(arr, cnt), nf
 
     def pdws(self, fs, fc=0.0, sampleStartTime=0.0, SNR_THRESHOLD=15.0, sat_level=0.9999,
              reproduce_phase_bug=False, TRAILING_EDGE_THRESHOLD=None):
@@ -418,5 +450,5 @@ def spectrogram_my_iq(rec):
     return {"power": np.abs(s) ** 2, "f_hz": f + rec.fc, "t_s": t}
 
 
-__all__ = ["IqRecording", "read_iq", "write_iq", "design_prototype", "Channelizer", "unpack_ptr",
+__all__ = ["PdwTable", "IqRecording", "read_iq", "write_iq", "design_prototype", "Channelizer", "unpack_ptr",
            "create_pdws_channelized", "create_pdws", "predict_event", "event_peak_time", "next_event_time", "stft", "spectrogram_my_iq", "ChannelizerError"]

@@ -561,7 +561,8 @@ void chz_destroy(chz_t* h) {
   h->cluster_ring.release();
   h->pipe_ctrl.release();
   for (int i = 0; i < 4; i++) { if (h->ev_fir[i]) cudaEventDestroy(h->ev_fir[i]); if (h->ev_fft[i]) cudaEventDestroy(h->ev_fft[i]); }
-  for (chzi::Scratch* sc : {&h->pdw_hist, &h->pdw_sel, &h->pdw_thr, &h->pdw_cnt, &h->pdw_ev, &h->pdw_pin, &h->pdw_pout, &h->pdw_code, &h->pdw_nf}) sc->release();
+  for (chzi::Scratch* sc : {&h->pdw_hist, &h->pdw_sel, &h->pdw_thr, &h->pdw_cnt, &h->pdw_ev, &h->pdw_pin, &h->pdw_pout, &h->pdw_code, &h->pdw_nf, &h->pdw_fast}) sc->release();
+  if (h->pdw_stage_host) cudaFreeHost(h->pdw_stage_host);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -591,6 +592,7 @@ int chz_set_option(chz_t* h, int opt, int64_t value) {
   switch (opt) {
     case CHZ_OPT_RETAIN: h->retain = value != 0; return CHZ_OK;
     case CHZ_OPT_CHUNK_ROWS: if (value < 0) return CHZ_EINVAL; h->chunk_rows = value; return CHZ_OK;
+    case CHZ_OPT_PDW_EVENT_PATH: h->pdw_event_path = value != 0; return CHZ_OK;
     case CHZ_OPT_FORCE_PATH: {
       bool ok = false;   // a path this build does not contain, or that has no kernel for the handle's (M, taps), is refused here
       switch (value) {

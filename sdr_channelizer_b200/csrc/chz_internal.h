@@ -95,8 +95,12 @@ struct chz {
   uint64_t launches = 0;
 
   // PDW scratch (histograms, select state, thresholds, edge events, pulse lists)
-  chzi::Scratch pdw_hist, pdw_sel, pdw_thr, pdw_cnt, pdw_ev, pdw_pin, pdw_pout, pdw_code, pdw_nf;
+  chzi::Scratch pdw_hist, pdw_sel, pdw_thr, pdw_cnt, pdw_ev, pdw_pin, pdw_pout, pdw_code, pdw_nf, pdw_fast;
   uint64_t pdw_ev_cap = 1ull << 20;
+  uint64_t pdw_pulse_cap = 1ull << 16;      // device-side pulse list of the one-GPU extractor (grows on demand)
+  bool pdw_event_path = false;              // CHZ_OPT_PDW_EVENT_PATH
+  void* pdw_stage_host = nullptr;           // pinned landing zone of its single device-to-host copy
+  size_t pdw_stage_bytes = 0;
 
   // PDW results of the last run
   std::vector<double> noise_floor;      // natural channel order

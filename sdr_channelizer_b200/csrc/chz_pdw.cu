@@ -82,9 +82,14 @@ __global__ void __launch_bounds__(256) k_hist(const float2* __restrict__ y, long
 }
 
 // one block per channel: find the bucket holding each wanted rank, fix its bits, reduce the rank
+struct Thr { float ge, le; };   // ge = smallest float >= the leading threshold, le = largest float <= the trailing one
+__device__ __forceinline__ void thresholds_of(const SelState& s, double scale, double scale_lo, Thr* thr, double* nf);
+
+// thr != NULL (last pass of the one-GPU extractor): the noise floor and the thresholds are derived right here,
+// which saves the k_thresholds launch
 __global__ void __launch_bounds__(256) k_select(uint32_t* __restrict__ hist, SelState* __restrict__ st, int pass,
-                                                uint32_t rank_lo, uint32_t rank_hi) {
-  __shared__ uint32_t part[256];
+                                                uint32_t rank_lo, uint32_t rank_hi, double scale, double scale_lo,
+                                                Thr* __restrict__ thr, double* __restrict__ nf) {
   __shared__ uint32_t res_bin[2], res_rank[2];
   const int ch = blockIdx.x;
   SelState s;
@@ -92,27 +97,52 @@ __global__ void __launch_bounds__(256) k_select(uint32_t* __restrict__ hist, Sel
   else s = st[ch];
   const bool split = pass > 0 && s.prefix[0] != s.prefix[1];
   const int nb = pass == 2 ? 512 : kBins, per = nb / 256;
+  // 256 partial sums per slot, then warp `slot` finds the bucket that holds the wanted rank with a prefix sum
+  // across its lanes (one thread walking 256 partial sums took 10-15 us per pass)
+  __shared__ uint32_t part2[2][256];
   for (int slot = 0; slot < 2; slot++) {
-    uint32_t* hrow = hist + ((size_t)ch * 2 + ((slot == 1 && split) ? 1 : 0)) * kBins;
+    const uint32_t* hrow = hist + ((size_t)ch * 2 + ((slot == 1 && split) ? 1 : 0)) * kBins;
     uint32_t loc = 0;
     for (int i = 0; i < per; i++) loc += hrow[threadIdx.x * per + i];
-    part[threadIdx.x] = loc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t acc = 0, want = s.rank[slot];
-      int t = 0;
-      for (; t < 255; t++) { if (acc + part[t] > want) break; acc += part[t]; }
+    part2[slot][threadIdx.x] = loc;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < 2) {
+    const int slot = warp;
+    const uint32_t* hrow = hist + ((size_t)ch * 2 + ((slot == 1 && split) ? 1 : 0)) * kBins;
+    const uint32_t want = s.rank[slot];
+    uint32_t c[8], sum = 0;
+    #pragma unroll
+    for (int j = 0; j < 8; j++) { c[j] = part2[slot][lane * 8 + j]; sum += c[j]; }
+    uint32_t incl = sum;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const uint32_t excl = incl - sum;
+    const bool here = excl <= want && want < incl;
+    const unsigned any = __ballot_sync(0xffffffffu, here);
+    if (here || (any == 0 && lane == 31)) {          // no lane qualifies only if want >= total: clamp to the last bucket
+      uint32_t acc = excl;
+      int t = lane * 8;
+      #pragma unroll
+      for (int j = 0; j < 7; j++) {
+        if (t == lane * 8 + j) { if (acc + c[j] > want) { /* found */ } else { acc += c[j]; t++; } }
+      }
       int b = t * per;
       for (; b < t * per + per - 1; b++) { if (acc + hrow[b] > want) break; acc += hrow[b]; }
       res_bin[slot] = (uint32_t)b;
       res_rank[slot] = want - acc;
     }
-    __syncthreads();
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
     const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
     for (int slot = 0; slot < 2; slot++) { s.prefix[slot] |= res_bin[slot] << shift; s.rank[slot] = res_rank[slot]; }
     st[ch] = s;
+    if (thr) thresholds_of(s, scale, scale_lo, thr + ch, nf + ch);
   }
   __syncthreads();
   // clear both histogram rows of this channel for the next pass
@@ -124,8 +154,6 @@ __global__ void __launch_bounds__(256) k_select(uint32_t* __restrict__ hist, Sel
 // mag <= le (le = largest float <= T_trail).  The channelized script uses one threshold for both
 // (create_pdws_channelized.m:88,94: T_trail == T_lead, ge/le bracket it); the wideband script uses
 // hysteresis (create_pdws.m:45-47,58,63: 18 dB up, 3 dB down => le < ge).
-struct Thr { float ge, le; };
-
 // Noise floor and thresholds (:73-75) from the selected order statistics, in double like the script, then
 // bracketed by floats: ge = smallest float >= T_lead, le = largest float <= T_trail (so the fp32 comparisons
 // of k_detect decide exactly like the double comparison would).  On the device so that the extractor does
@@ -140,28 +168,44 @@ __device__ __forceinline__ float float_le(double t) {
   if ((double)f > t) f = f == 0.f ? __uint_as_float(0x80000001u) : (f > 0.f ? __uint_as_float(__float_as_uint(f) - 1u) : __uint_as_float(__float_as_uint(f) + 1u));
   return f;
 }
+__device__ __forceinline__ void thresholds_of(const SelState& s, double scale, double scale_lo, Thr* thr, double* nf) {
+  const double lo = (double)__uint_as_float(s.prefix[0]), hi = (double)__uint_as_float(s.prefix[1]);
+  const double v = 0.5 * (lo + hi);                      // MATLAB median: mean of the two middle values
+  *nf = v;
+  Thr t;
+  t.ge = float_ge(v * scale);
+  t.le = float_le(v * scale_lo);
+  *thr = t;
+}
 __global__ void k_thresholds(const SelState* __restrict__ st, int M, double scale, double scale_lo, Thr* __restrict__ thr,
                              double* __restrict__ nf) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= M) return;
-  const double lo = (double)__uint_as_float(st[k].prefix[0]), hi = (double)__uint_as_float(st[k].prefix[1]);
-  const double v = 0.5 * (lo + hi);                      // MATLAB median: mean of the two middle values
-  nf[k] = v;
-  Thr t;
-  t.ge = float_ge(v * scale);
-  t.le = float_le(v * scale_lo);
-  thr[k] = t;
+  thresholds_of(st[k], scale, scale_lo, thr + k, nf + k);
 }
 
 // Lanes walk channels (coalesced 8-byte loads of a row), all lanes advance row by row through the same
 // chunk, so a warp ballot per row tells whether any channel saw an edge; one atomic per warp reserves
 // the slots and every lane with an edge writes at its ballot rank.
 // event = (shifted channel << 40) | (1-based row << 1) | (1 = trailing edge)
+//
+// PULSES (one-GPU extractor): instead of edge events the kernel emits finished pulses.  A trailing edge knows its
+// leading edge when that lay in the same chunk.  Otherwise the pulse goes out with toa = 0 and the statistics kernel
+// resolves it from the per-(chunk, channel) summaries written here -- the last row <= le of the chunk and the first
+// row >= ge after it -- walking back one 64-row chunk per step (walking back row by row inside this kernel made the
+// warps that sit in a long pulse the tail of the launch: 53 us against 17 us for everybody else).  No sort and no
+// pairing on the host, so the per-pulse statistics kernel can follow without a round trip.  The rare case the look-back
+// cannot decide locally -- a sample exactly equal to a single representable threshold, which toggles the state
+// (:88/:94) -- raises count[1] and the host falls back to the event path.
+struct PulseIn { unsigned long long toa, end; uint32_t k, kph; };   // rows 1-based, natural channels
+
+template <bool PULSES>
 __global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, long long nrows, int M,
                                                 const Thr* __restrict__ thr, int chunk_rows,
                                                 const uint8_t* __restrict__ entry, unsigned long long row_offset,
                                                 unsigned long long* __restrict__ events,
-                                                unsigned long long cap, unsigned long long* __restrict__ count) {
+                                                unsigned long long cap, unsigned long long* __restrict__ count,
+                                                int kph_fixed, uint2* __restrict__ summ) {
   const int lanes_ch = M < 32 ? M : 32;                   // channels per warp
   const int streams = 32 / lanes_ch;                      // independent row chunks inside one warp (M < 32)
   const int lane = threadIdx.x & 31;
@@ -188,17 +232,20 @@ __global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, lo
   // toggles it (:88 uses >=, :94 uses <= on the same value).  `entry` (time shards, per natural channel) is
   // the state the previous shard left behind; NULL = the FSM starts inactive (:83).
   bool active = entry ? entry[ch] != 0 : false;
+  long long lead = -1;                                     // PULSES: 0-based row of the open pulse's leading edge
   if (live && r0 > 0) {
     bool flips = false;
-    for (long long j = r0 - 1; j >= 0; j--) {
+    long long j = r0 - 1;
+    for (; j >= 0; j--) {
       const float m = mag_of(y[j * M + ch]);
-      if (exact && m == t.ge) { flips = !flips; continue; }
+      if (exact && m == t.ge) { flips = !flips; if (PULSES) count[1] = 1; continue; }
       if (m >= t.ge) { active = true; break; }
       if (m <= t.le) { active = false; break; }
     }
     active = active != flips;
   }
-  constexpr int UN = 8;                                    // rows fetched ahead of the (sequential) state machine
+  constexpr int UN = PULSES ? 16 : 8;                      // rows fetched ahead of the (sequential) state machine
+  uint32_t last_below = 0xFFFFFFFFu, first_above = 0xFFFFFFFFu;   // PULSES: chunk summary (rows of this launch)
   for (int i0 = 0; i0 < chunk_rows; i0 += UN) {            // lock-step over the chunk
     float2 v[UN];
     #pragma unroll
@@ -212,8 +259,13 @@ __global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, lo
       bool ev = false;
       if (live && r < r1) {
         const float m = mag_of(v[u]);
-        if (!active) { if (m >= t.ge) { active = true; ev = true; } }     // leading edge (:88)
-        else if (m <= t.le) { active = false; ev = true; }                // trailing edge (:94)
+        if (PULSES) {
+          if (exact && m == t.ge) count[1] = 1;
+          if (m <= t.le) { last_below = (uint32_t)r; first_above = 0xFFFFFFFFu; }
+          else if (m >= t.ge && first_above == 0xFFFFFFFFu) first_above = (uint32_t)r;
+        }
+        if (!active) { if (m >= t.ge) { active = true; ev = !PULSES; lead = r; } }   // leading edge (:88)
+        else if (m <= t.le) { active = false; ev = true; }                            // trailing edge (:94)
       }
       const unsigned ball = __ballot_sync(0xffffffffu, ev);
       if (ball) {
@@ -222,11 +274,21 @@ __global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, lo
         base = __shfl_sync(0xffffffffu, base, 0);
         if (ev) {
           const unsigned long long slot = base + __popc(ball & ((1u << lane) - 1));
-          if (slot < cap) events[slot] = (chs << 40) | (((unsigned long long)(r + 1) + row_offset) << 1) | (active ? 0ull : 1ull);
+          if (PULSES) {
+            if (slot < cap) {
+              PulseIn p;
+              p.toa = lead >= 0 ? (unsigned long long)(lead + 1) + row_offset : 0ull; p.end = (unsigned long long)(r + 1) + row_offset;
+              p.k = (uint32_t)ch; p.kph = kph_fixed >= 0 ? (uint32_t)kph_fixed : (uint32_t)ch;
+              *(PulseIn*)((unsigned char*)events + slot * (sizeof(PulseIn) + 24)) = p;   // slot of a {PulseIn, PulseOut} record
+            }
+          } else if (slot < cap) {
+            events[slot] = (chs << 40) | (((unsigned long long)(r + 1) + row_offset) << 1) | (active ? 0ull : 1ull);
+          }
         }
       }
     }
   }
+  if (PULSES && live) summ[chunk * M + ch] = make_uint2(last_below, first_above);
 }
 
 // State a shard leaves behind, per natural channel, as a function of the state it was entered with:
@@ -250,8 +312,8 @@ __global__ void __launch_bounds__(128) k_exit_state(const float2* __restrict__ y
 }
 
 // ---- per-pulse statistics ----------------------------------------------------------------------------
-struct PulseIn { unsigned long long toa, end; uint32_t k, kph; };   // rows 1-based, natural channels
 struct PulseOut { float amp_lo, amp_hi, pd_lo, pd_hi; uint32_t sat, pad; };
+static_assert(sizeof(PulseOut) == 24 && sizeof(PulseIn) == 24, "k_detect<true> writes PulseIn at a stride of sizeof(PulseIn) + sizeof(PulseOut)");
 
 __device__ __forceinline__ uint32_t fkey(float f) {      // order-preserving map float -> uint32
   const uint32_t b = __float_as_uint(f);
@@ -340,14 +402,43 @@ __device__ void block_select2(KeyF key, unsigned long long n, unsigned long long
 
 constexpr int kPulseCap = 5632;   // rows of a pulse held in shared memory (8 B per row: 44 KB)
 
-__global__ void __launch_bounds__(128) k_pulse_stats(const float2* __restrict__ y, long long M, double sat_level,
-                                                     unsigned long long row0,
-                                                     const PulseIn* __restrict__ in, PulseOut* __restrict__ outp) {
+// npulses_dev != NULL: the pulse count lives on the device (k_detect<true> has just written it) and the blocks
+// stride over the list; otherwise one block per pulse of a host-built list (n_host pulses).
+template <int STRIDE>   // bytes between consecutive PulseIn (and between consecutive PulseOut) records
+__device__ __forceinline__ void pulse_stats_body(const float2* __restrict__ y, long long M, double sat_level,
+                                                 unsigned long long row0,
+                                                 const PulseIn* __restrict__ in, PulseOut* __restrict__ outp,
+                                                 const unsigned long long* __restrict__ npulses_dev,
+                                                 unsigned long long n_host, unsigned long long cap,
+                                                 const uint2* __restrict__ summ, int chunk_rows) {
+  __shared__ unsigned long long sh_toa;
   __shared__ uint32_t h0[256], h1[256], res[2];
   __shared__ unsigned long long sh_rank[2];
   __shared__ int sh_sat;
   __shared__ uint32_t kmag[kPulseCap], kpd[kPulseCap];      // order-preserving keys of |y| and of the phase differences
-  const PulseIn p = in[blockIdx.x];
+  unsigned long long total = npulses_dev ? *npulses_dev : n_host;
+  if (total > cap) total = cap;
+  if (summ && npulses_dev[1]) return;      // k_detect<true> asked for the event path: its pulse list is not to be trusted
+  for (unsigned long long pi = blockIdx.x; pi < total; pi += gridDim.x) {
+  __syncthreads();                                           // shared state of the previous pulse is no longer read
+  PulseIn p = *(const PulseIn*)((const unsigned char*)in + pi * STRIDE);
+  if (summ && p.toa == 0) {
+    // the pulse was already open when its trailing edge's chunk began: its leading edge is the first row >= ge
+    // after the last row <= le before that chunk (k_detect<true>'s summaries, one 64-row chunk per step)
+    if (threadIdx.x == 0) {
+      uint32_t lead = 0xFFFFFFFFu;
+      for (long long c = (long long)((p.end - 1) / chunk_rows) - 1; c >= 0; c--) {
+        const uint2 sm = summ[c * M + p.k];
+        if (sm.y != 0xFFFFFFFFu) lead = sm.y;
+        if (sm.x != 0xFFFFFFFFu) break;
+      }
+      sh_toa = lead == 0xFFFFFFFFu ? 0ull : (unsigned long long)lead + 1;
+      ((PulseIn*)((unsigned char*)in + pi * STRIDE))->toa = sh_toa;
+    }
+    __syncthreads();
+    p.toa = sh_toa;
+  }
+  if (p.toa == 0 || p.toa > p.end) continue;                 // (never for a consistent list; keeps a bad one from reading out of bounds)
   const unsigned long long a = p.toa - 1 - row0, b = p.end - 1 - row0;   // 0-based inclusive rows of y
   if (threadIdx.x == 0) sh_sat = 0;
   __syncthreads();
@@ -389,7 +480,22 @@ __global__ void __launch_bounds__(128) k_pulse_stats(const float2* __restrict__ 
                      }, n2, (n2 - 1) / 2, n2 / 2, h0, h1, res, sh_rank);
   o.pd_lo = fkey_inv(res[0]); o.pd_hi = fkey_inv(res[1]);
   o.sat = (uint32_t)sh_sat; o.pad = 0;
-  if (threadIdx.x == 0) outp[blockIdx.x] = o;
+  if (threadIdx.x == 0) *(PulseOut*)((unsigned char*)outp + pi * STRIDE) = o;
+  }
+}
+__global__ void __launch_bounds__(128) k_pulse_stats(const float2* __restrict__ y, long long M, double sat_level, unsigned long long row0,
+                                                     const PulseIn* __restrict__ in, PulseOut* __restrict__ outp,
+                                                     const unsigned long long* __restrict__ npulses_dev,
+                                                     unsigned long long n_host, unsigned long long cap) {
+  pulse_stats_body<(int)sizeof(PulseIn)>(y, M, sat_level, row0, in, outp, npulses_dev, n_host, cap, nullptr, 0);
+}
+// records laid out as {PulseIn, PulseOut} pairs (the one-GPU extractor's device-side pulse list)
+__global__ void __launch_bounds__(128) k_pulse_stats_rec(const float2* __restrict__ y, long long M, double sat_level, void* recs,
+                                                         const unsigned long long* __restrict__ npulses_dev, unsigned long long cap,
+                                                         const uint2* __restrict__ summ, int chunk_rows) {
+  pulse_stats_body<(int)(sizeof(PulseIn) + sizeof(PulseOut))>(y, M, sat_level, 0ull, (const PulseIn*)recs,
+                                                             (PulseOut*)((unsigned char*)recs + sizeof(PulseIn)), npulses_dev, 0ull, cap,
+                                                             summ, chunk_rows);
 }
 
 // ---- host driver ---------------------------------------------------------------------------------------
@@ -414,7 +520,7 @@ static int pdw_hist_pass(::chz* h, const float2* y, uint64_t nrows, int pass) {
   uint32_t* d_hist = (uint32_t*)h->pdw_hist.p;
   if (pass == 0) CHZ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)M * 2 * kBins * sizeof(uint32_t), st));
   if (nrows == 0) return CHZ_OK;
-  long long ychunks = (h->sm_count * 4 + (M + 3) / 4 - 1) / ((M + 3) / 4);
+  long long ychunks = (h->sm_count * 8 + (M + 3) / 4 - 1) / ((M + 3) / 4);
   const long long max_chunks = (long long)((nrows + 255) / 256);
   if (ychunks > max_chunks) ychunks = max_chunks;
   if (ychunks < 1) ychunks = 1;
@@ -427,10 +533,21 @@ static int pdw_hist_pass(::chz* h, const float2* y, uint64_t nrows, int pass) {
 
 // fix the next bits of both middle order statistics from the (summed) histogram; total_rows = rows of the
 // WHOLE recording
-static int pdw_select_pass(::chz* h, int pass, uint64_t total_rows) {
+static void threshold_scales(const chz_pdw_params_t* prm, double* scale, double* scale_lo) {
+  *scale = std::pow(10.0, prm->snr_threshold_db / 10.0);
+  // create_pdws.m:47: TRAILING_EDGE_THRESHOLD = NOISE_FLOOR*10^(3/10); never above the leading threshold
+  const bool hyst = prm->use_trailing_threshold != 0 && prm->trailing_snr_threshold_db < prm->snr_threshold_db;
+  *scale_lo = hyst ? std::pow(10.0, prm->trailing_snr_threshold_db / 10.0) : *scale;
+}
+
+// prm != NULL on the last pass: noise floor -> nf_dev and thresholds -> h->pdw_thr in the same launch
+static int pdw_select_pass(::chz* h, int pass, uint64_t total_rows, const chz_pdw_params_t* prm = nullptr, double* nf_dev = nullptr) {
   if (total_rows == 0 || total_rows > 0xFFFFFFFFull) return CHZ_EINVAL;
   const uint32_t rank_lo = (uint32_t)((total_rows - 1) / 2), rank_hi = (uint32_t)(total_rows / 2);
-  k_select<<<h->M, 256, 0, h->stream>>>((uint32_t*)h->pdw_hist.p, (SelState*)h->pdw_sel.p, pass, rank_lo, rank_hi);
+  double scale = 0.0, scale_lo = 0.0;
+  if (prm) threshold_scales(prm, &scale, &scale_lo);
+  k_select<<<h->M, 256, 0, h->stream>>>((uint32_t*)h->pdw_hist.p, (SelState*)h->pdw_sel.p, pass, rank_lo, rank_hi, scale, scale_lo,
+                                         prm ? (Thr*)h->pdw_thr.p : nullptr, nf_dev);
   h->launches++;
   CHZ_CUDA(cudaGetLastError());
   return CHZ_OK;
@@ -441,10 +558,8 @@ static int pdw_select_pass(::chz* h, int pass, uint64_t total_rows) {
 static int pdw_thresholds(::chz* h, const chz_pdw_params_t* prm, bool fetch) {
   const int M = (int)h->M;
   cudaStream_t st = h->stream;
-  const double scale = std::pow(10.0, prm->snr_threshold_db / 10.0);
-  // create_pdws.m:47: TRAILING_EDGE_THRESHOLD = NOISE_FLOOR*10^(3/10); never above the leading threshold
-  const bool hyst = prm->use_trailing_threshold != 0 && prm->trailing_snr_threshold_db < prm->snr_threshold_db;
-  const double scale_lo = hyst ? std::pow(10.0, prm->trailing_snr_threshold_db / 10.0) : scale;
+  double scale, scale_lo;
+  threshold_scales(prm, &scale, &scale_lo);
   k_thresholds<<<(M + 127) / 128, 128, 0, st>>>((const SelState*)h->pdw_sel.p, M, scale, scale_lo, (Thr*)h->pdw_thr.p,
                                                 (double*)h->pdw_nf.p);
   h->launches++;
@@ -492,8 +607,8 @@ static int pdw_detect(::chz* h, const float2* y, uint64_t nrows, uint64_t row_of
     unsigned long long* d_cnt = (unsigned long long*)h->pdw_ev.p;
     unsigned long long* d_ev = d_cnt + 1;
     CHZ_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
-    k_detect<<<(unsigned)blocks, 256, 0, st>>>(y, (long long)nrows, M, (const Thr*)h->pdw_thr.p, chunk_rows, d_entry,
-                                               (unsigned long long)row_offset, d_ev, cap, d_cnt);
+    k_detect<false><<<(unsigned)blocks, 256, 0, st>>>(y, (long long)nrows, M, (const Thr*)h->pdw_thr.p, chunk_rows, d_entry,
+                                                      (unsigned long long)row_offset, d_ev, cap, d_cnt, -1, nullptr);
     h->launches++;
     CHZ_CUDA(cudaGetLastError());
     if (fetch_nf()) return CHZ_ECUDA;
@@ -558,13 +673,34 @@ static void pdw_pair(std::vector<unsigned long long>& ev, uint32_t M, bool phase
   }
 }
 
+// one record (:97-128) from a pulse's edges and its device-side statistics
+static chz_pdw_t make_record(const ::chz* h, const chz_pdw_params_t* prm, uint32_t k, uint64_t toa_row, uint64_t end_row,
+                             const PulseOut& o) {
+  const int M = (int)h->M;
+  const double fs_dec = prm->fs_sps / (double)h->D;        // :62
+  chz_pdw_t r;
+  memset(&r, 0, sizeof r);
+  const uint32_t c = (k + (uint32_t)(M / 2)) % (uint32_t)M;
+  const double bin_freq = ((double)c - (double)(M / 2)) * prm->fs_sps / (double)M;   // :42 on shifted columns
+  const double nf = h->noise_floor[k];
+  const double med_pd = 0.5 * ((double)o.pd_lo + (double)o.pd_hi);
+  r.toa_s = ((double)toa_row / fs_dec) + prm->t0;                                     // :98
+  r.amp = 0.5 * ((double)o.amp_lo + (double)o.amp_hi);                                // :101
+  r.snr_db = 10.0 * std::log10(r.amp / nf);                                           // :105
+  r.pw_s = (double)(end_row - toa_row) / fs_dec;                                      // :110
+  r.freq_hz = (prm->fc_hz + bin_freq) + (fs_dec / (360.0 / med_pd));                  // :80, :122
+  r.noise_floor = nf;
+  r.channel = c; r.channel_natural = k;
+  r.toa_row = toa_row; r.end_row = end_row; r.saturated = o.sat;
+  return r;
+}
+
 // per-pulse medians and saturation (:97-122) and the records (:97-128) for pulses whose rows all lie in
 // y (leading dimension ld, row 0 = 1-based row row_offset + 1 of the run; columns p.col / p.col_phase)
 static int pdw_records(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t ld, uint64_t row_offset,
                        const chz_pulse_t* pulses, size_t n, chz_pdw_t* out) {
   if (n == 0) return CHZ_OK;
   if (h->noise_floor.size() != h->M) return CHZ_ESTATE;
-  const int M = (int)h->M;
   cudaStream_t st = h->stream;
   std::vector<PulseIn> pin(n);
   for (size_t i = 0; i < n; i++) {
@@ -577,41 +713,104 @@ static int pdw_records(::chz* h, const chz_pdw_params_t* prm, const float2* y, u
   PulseIn* d_pin = (PulseIn*)h->pdw_pin.p;
   PulseOut* d_pout = (PulseOut*)h->pdw_pout.p;
   CHZ_CUDA(cudaMemcpyAsync(d_pin, pin.data(), n * sizeof(PulseIn), cudaMemcpyHostToDevice, st));
-  k_pulse_stats<<<(unsigned)n, 128, 0, st>>>(y, (long long)ld, prm->sat_level, (unsigned long long)row_offset, d_pin, d_pout);
+  k_pulse_stats<<<(unsigned)n, 128, 0, st>>>(y, (long long)ld, prm->sat_level, (unsigned long long)row_offset, d_pin, d_pout,
+                                             nullptr, (unsigned long long)n, (unsigned long long)n);
   h->launches++;
   CHZ_CUDA(cudaGetLastError());
   std::vector<PulseOut> pout(n);
   CHZ_CUDA(cudaMemcpyAsync(pout.data(), d_pout, n * sizeof(PulseOut), cudaMemcpyDeviceToHost, st));
   CHZ_CUDA(cudaStreamSynchronize(st));
-  // records (:97-128)
-  const double fs_dec = prm->fs_sps / (double)h->D;        // :62
-  for (size_t i = 0; i < n; i++) {
-    const chz_pulse_t& p = pulses[i];
-    const PulseOut& o = pout[i];
-    chz_pdw_t r;
-    memset(&r, 0, sizeof r);
-    const uint32_t k = p.channel_natural;
-    const uint32_t c = (k + (uint32_t)(M / 2)) % (uint32_t)M;
-    const double bin_freq = ((double)c - (double)(M / 2)) * prm->fs_sps / (double)M;   // :42 on shifted columns
-    const double nf = h->noise_floor[k];
-    const double med_pd = 0.5 * ((double)o.pd_lo + (double)o.pd_hi);
-    r.toa_s = ((double)p.toa_row / fs_dec) + prm->t0;                                   // :98
-    r.amp = 0.5 * ((double)o.amp_lo + (double)o.amp_hi);                                // :101
-    r.snr_db = 10.0 * std::log10(r.amp / nf);                                           // :105
-    r.pw_s = (double)(p.end_row - p.toa_row) / fs_dec;                                  // :110
-    r.freq_hz = (prm->fc_hz + bin_freq) + (fs_dec / (360.0 / med_pd));                  // :80, :122
-    r.noise_floor = nf;
-    r.channel = c; r.channel_natural = k;
-    r.toa_row = p.toa_row; r.end_row = p.end_row; r.saturated = o.sat;
-    out[i] = r;
-  }
+  for (size_t i = 0; i < n; i++) out[i] = make_record(h, prm, pulses[i].channel_natural, pulses[i].toa_row, pulses[i].end_row, pout[i]);
   return CHZ_OK;
+}
+
+// One-GPU extractor without a host round trip between its stages: median passes -> thresholds (fused into the last
+// select) -> k_detect<true> (finished pulses, device-side list and count) -> k_pulse_stats striding over that list ->
+// ONE copy of count + noise floor + pulses + statistics into pinned memory -> ONE synchronisation.  The host then
+// only builds the records and orders them as the script does (:79,85: shifted channel ascending, then time).
+// Returns 1 when the kernel asked for the event path (a sample exactly on a single representable threshold).
+struct PulseRec { PulseIn in; PulseOut out; };
+constexpr unsigned long long kStageFirst = 4096;     // pulse records fetched together with the count
+
+static int pdw_extract_fast(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t nrows) {
+  const int M = (int)h->M;
+  cudaStream_t st = h->stream;
+  int rc = pdw_buffers(h);
+  if (rc) return rc;
+  const size_t head = 16 + (size_t)M * sizeof(double);                    // [count, fallback flag][noise floor]
+  if (!h->pdw_stage_host || h->pdw_stage_bytes < head + kStageFirst * sizeof(PulseRec)) {
+    if (h->pdw_stage_host) cudaFreeHost(h->pdw_stage_host);
+    h->pdw_stage_host = nullptr;
+    h->pdw_stage_bytes = head + kStageFirst * sizeof(PulseRec);
+    CHZ_CUDA(cudaMallocHost(&h->pdw_stage_host, h->pdw_stage_bytes));
+  }
+  for (int pass = 0; pass < 3; pass++) {
+    if ((rc = pdw_hist_pass(h, y, nrows, pass))) return rc;
+    if (pass < 2 && (rc = pdw_select_pass(h, pass, nrows))) return rc;
+  }
+  const int chunk_rows = 64;
+  const long long nchunks = ((long long)nrows + chunk_rows - 1) / chunk_rows;
+  const int lanes_ch = M < 32 ? M : 32, streams = 32 / lanes_ch, ch_groups = (M + 31) / 32;
+  const long long warps = ((nchunks + streams - 1) / streams) * ch_groups;
+  const long long blocks = (warps + 7) / 8;
+  CHZ_CUDA(h->pdw_ev.reserve((size_t)nchunks * M * sizeof(uint2)));       // chunk summaries (the event list is not used here)
+  uint2* d_summ = (uint2*)h->pdw_ev.p;
+  const int kbug = prm->reproduce_phase_bug ? (int)((0 + (M + 1) / 2) % M) : -1;   // natural channel of shifted column 1 (:114)
+  bool selected = false;
+  for (;;) {
+    const unsigned long long cap = h->pdw_pulse_cap;
+    CHZ_CUDA(h->pdw_fast.reserve(head + cap * sizeof(PulseRec)));
+    unsigned char* base = (unsigned char*)h->pdw_fast.p;
+    unsigned long long* d_cnt = (unsigned long long*)base;
+    double* d_nf = (double*)(base + 16);
+    PulseRec* d_rec = (PulseRec*)(base + head);
+    if (!selected) {      // last select + thresholds, writing the noise floor next to the counters
+      if ((rc = pdw_select_pass(h, 2, nrows, prm, d_nf))) return rc;
+      selected = true;
+    } else {              // rerun with a larger list: the noise floor moved with the buffer
+      CHZ_CUDA(cudaMemcpyAsync(d_nf, h->noise_floor.data(), sizeof(double) * M, cudaMemcpyHostToDevice, st));
+    }
+    CHZ_CUDA(cudaMemsetAsync(d_cnt, 0, 16, st));
+    k_detect<true><<<(unsigned)blocks, 256, 0, st>>>(y, (long long)nrows, M, (const Thr*)h->pdw_thr.p, chunk_rows, nullptr, 0ull,
+                                                     (unsigned long long*)d_rec, cap, d_cnt, kbug, d_summ);
+    h->launches++;
+    CHZ_CUDA(cudaGetLastError());
+    // PulseRec interleaves input and output, so detect writes .in of slot i and the statistics kernel .out
+    static_assert(sizeof(PulseRec) == sizeof(PulseIn) + sizeof(PulseOut), "packed");
+    const unsigned sblocks = (unsigned)std::min<unsigned long long>(cap, (unsigned long long)h->sm_count * 8);
+    k_pulse_stats_rec<<<sblocks, 128, 0, st>>>(y, (long long)M, prm->sat_level, d_rec, d_cnt, cap, d_summ, chunk_rows);
+    h->launches++;
+    CHZ_CUDA(cudaGetLastError());
+    const unsigned long long first = std::min<unsigned long long>(cap, kStageFirst);
+    CHZ_CUDA(cudaMemcpyAsync(h->pdw_stage_host, base, head + first * sizeof(PulseRec), cudaMemcpyDeviceToHost, st));
+    CHZ_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long* hc = (const unsigned long long*)h->pdw_stage_host;
+    const unsigned long long n = hc[0];
+    memcpy(h->noise_floor.data(), (const unsigned char*)h->pdw_stage_host + 16, sizeof(double) * M);
+    if (hc[1]) return 1;                               // equality on a representable threshold: event path
+    if (n > cap) { h->pdw_pulse_cap = n + n / 4; continue; }
+    std::vector<PulseRec> recs(n);
+    const unsigned long long got = std::min(n, first);
+    if (got) memcpy(recs.data(), (const unsigned char*)h->pdw_stage_host + head, got * sizeof(PulseRec));
+    if (n > got) {
+      CHZ_CUDA(cudaMemcpyAsync(recs.data() + got, d_rec + got, (n - got) * sizeof(PulseRec), cudaMemcpyDeviceToHost, st));
+      CHZ_CUDA(cudaStreamSynchronize(st));
+    }
+    h->pdws.resize(n);
+    for (unsigned long long i = 0; i < n; i++)
+      h->pdws[i] = make_record(h, prm, recs[i].in.k, recs[i].in.toa, recs[i].in.end, recs[i].out);
+    std::sort(h->pdws.begin(), h->pdws.end(), [](const chz_pdw_t& a, const chz_pdw_t& b) {
+      return a.channel != b.channel ? a.channel < b.channel : a.toa_row < b.toa_row;
+    });
+    return CHZ_OK;
+  }
 }
 
 int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t nrows) {
   const int M = (int)h->M;
   // CHZ_PDW_TRACE=1: host wall-clock of each stage on stderr (debug aid)
   static const bool trace = std::getenv("CHZ_PDW_TRACE") != nullptr;
+  const bool events_only = h->pdw_event_path;   // CHZ_OPT_PDW_EVENT_PATH: always take the event path (A/B, tests)
   auto t_prev = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
     if (!trace) return;
@@ -623,17 +822,24 @@ int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t
   h->noise_floor.assign(M, NAN);
   if (nrows == 0) return CHZ_OK;
   int rc;
-  // 1. exact per-channel median of |y| (:73)
-  for (int pass = 0; pass < 3; pass++) {
-    if ((rc = pdw_hist_pass(h, y, nrows, pass))) return rc;
-    if ((rc = pdw_select_pass(h, pass, nrows))) return rc;
+  if (!events_only) {
+    rc = pdw_extract_fast(h, prm, y, nrows);
+    lap("fast path");
+    if (rc != 1) { if (rc) h->pdws.clear(); return rc; }
+    h->pdws.clear();                                 // fall through: thresholds and noise floor are already in place
+  } else {
+    // 1. exact per-channel median of |y| (:73)
+    for (int pass = 0; pass < 3; pass++) {
+      if ((rc = pdw_hist_pass(h, y, nrows, pass))) return rc;
+      if ((rc = pdw_select_pass(h, pass, nrows))) return rc;
+    }
+    lap("median");
+    // 2. thresholds (:74-75)
+    if ((rc = pdw_thresholds(h, prm, false))) return rc;
   }
-  lap("median");
-  // 2. thresholds (:74-75)
-  if ((rc = pdw_thresholds(h, prm, false))) return rc;
   // 3. edge events (:79-96); the noise floor comes back with the event count
   std::vector<unsigned long long> ev;
-  if ((rc = pdw_detect(h, y, nrows, 0, nullptr, ev, true))) return rc;
+  if ((rc = pdw_detect(h, y, nrows, 0, nullptr, ev, events_only))) return rc;
   lap("detect");
   // 4. pulses in the reference's order: shifted channel ascending, then time
   std::vector<chz_pulse_t> pulses;

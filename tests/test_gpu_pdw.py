@@ -92,6 +92,34 @@ def test_phase_bug_flag(orc):
         _compare(recs, orecs, 1e6, tol_rows=0)
 
 
+@pytest.mark.parametrize("M,seed,hyst", [(256, 100, False), (64, 102, False), (8, 104, False), (1, 105, True)])
+def test_single_sync_extractor_equals_event_path(M, seed, hyst):
+    """The one-GPU extractor emits finished pulses on the device (k_detect<true> -> k_pulse_stats over the device-side
+    list -> one copy, one synchronisation).  Its records must be byte-identical to those of the edge-event path
+    (events to the host, radix sort, pairing, second launch) it replaced and still falls back to."""
+    torch = _torch()
+    if M == 1:      # the wideband recipe of test_wideband_create_pdws_script: pulses thousands of rows long
+        fs = 10e6
+        x, _ = synth.pulsed_complex(400_000, fs, seed=77, sigma=0.004, amp=0.6)
+        iq = np.stack([np.clip(np.rint(x.real * 32768), -32768, 32767), np.clip(np.rint(x.imag * 32768), -32768, 32767)],
+                      axis=1).astype(np.int16)
+        bw = 16
+    else:
+        iq, bw, fs = synth.pulsed_int16(M * 9000, M=M, seed=seed)
+    taps = pkg.design_prototype(M, 16) if M > 1 else np.ones(1, np.float32)
+    kw = dict(SNR_THRESHOLD=18.0, TRAILING_EDGE_THRESHOLD=3.0) if hyst else {}
+    out = []
+    for event_path in (0, 1):
+        ch = pkg.Channelizer(M, taps=taps, retain=True)
+        ch.set_option(pkg.CHZ_OPT_PDW_EVENT_PATH, event_path)
+        ch(iq, bw)
+        recs, nf = ch.pdws(fs, 2.4e9, 17.0, **kw)
+        out.append((b"".join(bytes(r) for r in recs), nf.copy(), len(recs)))
+        ch.close()
+    assert out[0][2] == out[1][2] and out[0][2] >= 3
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+
+
 def test_no_pulses_and_empty():
     rng = np.random.default_rng(0)
     y = (rng.standard_normal((1000, 16)) + 1j * rng.standard_normal((1000, 16))).astype(np.complex64)
