@@ -256,16 +256,20 @@ class Channelizer:
 
     # -- PDWs ----------------------------------------------------------------------------------
     def _pdw_call(self, fn, params, *lead):
+        L = lib()
         n = C.c_uint64(0)
-        rc = fn(self._h, C.byref(params), *lead, None, 0, C.byref(n))
-        if rc not in (_lib.CHZ_OK, _lib.CHZ_ECAPACITY):
-            check(rc, "chz_pdws")
+        cap = max(256, 2 * getattr(self, "_last_pdw_count", 0))      # one call in the common case; a fresh array per call
+        arr = (Pdw * cap)()
+        rc = fn(self._h, C.byref(params), *lead, C.cast(arr, C.c_void_p), cap, C.byref(n))
         cnt = int(n.value)
-        arr = (Pdw * max(cnt, 1))()
-        if cnt:   # the run above cached its records in the handle; copy them out without recomputing
-            check(lib().chz_pdws_fetch(self._h, C.cast(arr, C.c_void_p), cnt, C.byref(n)), "chz_pdws_fetch")
+        if rc == _lib.CHZ_ECAPACITY:   # the run cached its records in the handle; copy them out without recomputing
+            arr = (Pdw * cnt)()
+            check(L.chz_pdws_fetch(self._h, C.cast(arr, C.c_void_p), cnt, C.byref(n)), "chz_pdws_fetch")
+        elif rc != _lib.CHZ_OK:
+            check(rc, "chz_pdws")
+        self._last_pdw_count = cnt
         nf = np.empty(self.NumFrequencyBands, dtype=np.float64)
-        check(lib().chz_pdw_noise_floor(self._h, nf.ctypes.data_as(C.c_void_p), len(nf)), "chz_pdw_noise_floor")
+        check(L.chz_pdw_noise_floor(self._h, nf.ctypes.data_as(C.c_void_p), len(nf)), "chz_pdw_noise_floor")
         return PdwTable(arr, cnt), nf
 
     def pdws(self, fs, fc=0.0, sampleStartTime=0.0, SNR_THRESHOLD=15.0, sat_level=0.9999,

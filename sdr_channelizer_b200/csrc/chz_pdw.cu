@@ -520,7 +520,10 @@ static int pdw_hist_pass(::chz* h, const float2* y, uint64_t nrows, int pass) {
   uint32_t* d_hist = (uint32_t*)h->pdw_hist.p;
   if (pass == 0) CHZ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)M * 2 * kBins * sizeof(uint32_t), st));
   if (nrows == 0) return CHZ_OK;
-  long long ychunks = (h->sm_count * 8 + (M + 3) / 4 - 1) / ((M + 3) / 4);
+  // one wave: 7 blocks of 256 threads fit an SM (32 KB of histogram each); a second, partial wave doubled the pass time on 100 ms files
+  long long ychunks = ((long long)h->sm_count * 7) / ((M + 3) / 4);
+  static const int hc_env = std::getenv("CHZ_PDW_HIST_CHUNKS") ? std::atoi(std::getenv("CHZ_PDW_HIST_CHUNKS")) : 0;   // tuning aid
+  if (hc_env > 0) ychunks = hc_env;
   const long long max_chunks = (long long)((nrows + 255) / 256);
   if (ychunks > max_chunks) ychunks = max_chunks;
   if (ychunks < 1) ychunks = 1;
@@ -730,7 +733,7 @@ static int pdw_records(::chz* h, const chz_pdw_params_t* prm, const float2* y, u
 // only builds the records and orders them as the script does (:79,85: shifted channel ascending, then time).
 // Returns 1 when the kernel asked for the event path (a sample exactly on a single representable threshold).
 struct PulseRec { PulseIn in; PulseOut out; };
-constexpr unsigned long long kStageFirst = 4096;     // pulse records fetched together with the count
+constexpr unsigned long long kStageFirst = 2048;     // pulse records fetched together with the count
 
 static int pdw_extract_fast(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t nrows) {
   const int M = (int)h->M;
@@ -744,11 +747,17 @@ static int pdw_extract_fast(::chz* h, const chz_pdw_params_t* prm, const float2*
     h->pdw_stage_bytes = head + kStageFirst * sizeof(PulseRec);
     CHZ_CUDA(cudaMallocHost(&h->pdw_stage_host, h->pdw_stage_bytes));
   }
+  static const bool gtrace = std::getenv("CHZ_PDW_TRACE") != nullptr;   // GPU time of each stage (CUDA events), debug aid
+  cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  auto mark = [&](int i) { if (gtrace) { if (!tev[i]) cudaEventCreate(&tev[i]); cudaEventRecord(tev[i], st); } };
+  mark(0);
   for (int pass = 0; pass < 3; pass++) {
     if ((rc = pdw_hist_pass(h, y, nrows, pass))) return rc;
     if (pass < 2 && (rc = pdw_select_pass(h, pass, nrows))) return rc;
+    if (pass == 0) mark(1);
   }
-  const int chunk_rows = 64;
+  static const int chunk_env = std::getenv("CHZ_PDW_CHUNK_ROWS") ? std::atoi(std::getenv("CHZ_PDW_CHUNK_ROWS")) : 0;   // tuning aid (multiple of 16)
+  const int chunk_rows = chunk_env > 0 ? chunk_env : 64;
   const long long nchunks = ((long long)nrows + chunk_rows - 1) / chunk_rows;
   const int lanes_ch = M < 32 ? M : 32, streams = 32 / lanes_ch, ch_groups = (M + 31) / 32;
   const long long warps = ((nchunks + streams - 1) / streams) * ch_groups;
@@ -770,6 +779,7 @@ static int pdw_extract_fast(::chz* h, const chz_pdw_params_t* prm, const float2*
     } else {              // rerun with a larger list: the noise floor moved with the buffer
       CHZ_CUDA(cudaMemcpyAsync(d_nf, h->noise_floor.data(), sizeof(double) * M, cudaMemcpyHostToDevice, st));
     }
+    mark(2);
     CHZ_CUDA(cudaMemsetAsync(d_cnt, 0, 16, st));
     k_detect<true><<<(unsigned)blocks, 256, 0, st>>>(y, (long long)nrows, M, (const Thr*)h->pdw_thr.p, chunk_rows, nullptr, 0ull,
                                                      (unsigned long long*)d_rec, cap, d_cnt, kbug, d_summ);
@@ -777,13 +787,23 @@ static int pdw_extract_fast(::chz* h, const chz_pdw_params_t* prm, const float2*
     CHZ_CUDA(cudaGetLastError());
     // PulseRec interleaves input and output, so detect writes .in of slot i and the statistics kernel .out
     static_assert(sizeof(PulseRec) == sizeof(PulseIn) + sizeof(PulseOut), "packed");
+    mark(3);
     const unsigned sblocks = (unsigned)std::min<unsigned long long>(cap, (unsigned long long)h->sm_count * 8);
     k_pulse_stats_rec<<<sblocks, 128, 0, st>>>(y, (long long)M, prm->sat_level, d_rec, d_cnt, cap, d_summ, chunk_rows);
     h->launches++;
     CHZ_CUDA(cudaGetLastError());
+    mark(4);
     const unsigned long long first = std::min<unsigned long long>(cap, kStageFirst);
     CHZ_CUDA(cudaMemcpyAsync(h->pdw_stage_host, base, head + first * sizeof(PulseRec), cudaMemcpyDeviceToHost, st));
+    mark(5);
     CHZ_CUDA(cudaStreamSynchronize(st));
+    if (gtrace) {
+      float ms[5];
+      for (int i = 0; i < 5; i++) cudaEventElapsedTime(&ms[i], tev[i], tev[i + 1]);
+      std::fprintf(stderr, "[chz pdw gpu] hist0+sel0 %.1f us | hist1..sel2 %.1f | detect %.1f | stats %.1f | copy %.1f\n", ms[0] * 1e3,
+                   ms[1] * 1e3, ms[2] * 1e3, ms[3] * 1e3, ms[4] * 1e3);
+      for (int i = 0; i < 6; i++) cudaEventDestroy(tev[i]);
+    }
     const unsigned long long* hc = (const unsigned long long*)h->pdw_stage_host;
     const unsigned long long n = hc[0];
     memcpy(h->noise_floor.data(), (const unsigned char*)h->pdw_stage_host + 16, sizeof(double) * M);
