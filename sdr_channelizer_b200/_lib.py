@@ -23,7 +23,7 @@ EXPORTS = [
     "chz_unpack_dev", "chz_fft_rows_dev",
     "chz_pdws", "chz_pdws_dev", "chz_pdws_fetch", "chz_pdw_noise_floor", "chz_retained", "chz_reserve_rows",
     "chz_kernel_launches", "chz_alloc_host", "chz_free_host",
-    "chz_pdw_shard_hist_dev", "chz_pdw_shard_select", "chz_pdw_shard_thresholds", "chz_pdw_shard_exit_state_dev",
+    "chz_pdw_shard_hist_dev", "chz_pdw_shard_select", "chz_pdw_shard_thresholds", "chz_pdw_shard_set_noise_floor", "chz_pdw_shard_exit_state_dev",
     "chz_pdw_shard_detect_dev", "chz_pdw_pair_events", "chz_pdw_shard_records_dev",
     "chz_event_peak_time", "chz_next_event_time",
 ]
@@ -116,6 +116,7 @@ def lib():
     L.chz_pdw_shard_hist_dev.argtypes = [vp, vp, u64, i32, C.POINTER(vp), pu64]; L.chz_pdw_shard_hist_dev.restype = i32
     L.chz_pdw_shard_select.argtypes = [vp, i32, u64]; L.chz_pdw_shard_select.restype = i32
     L.chz_pdw_shard_thresholds.argtypes = [vp, C.POINTER(PdwParams)]; L.chz_pdw_shard_thresholds.restype = i32
+    L.chz_pdw_shard_set_noise_floor.argtypes = [vp, C.POINTER(PdwParams), vp]; L.chz_pdw_shard_set_noise_floor.restype = i32
     L.chz_pdw_shard_exit_state_dev.argtypes = [vp, vp, u64, vp]; L.chz_pdw_shard_exit_state_dev.restype = i32
     L.chz_pdw_shard_detect_dev.argtypes = [vp, vp, u64, u64, vp, vp, u64, pu64]; L.chz_pdw_shard_detect_dev.restype = i32
     L.chz_pdw_pair_events.argtypes = [vp, u64, u32, u32, vp, u64, pu64]; L.chz_pdw_pair_events.restype = i32

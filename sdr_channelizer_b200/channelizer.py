@@ -332,6 +332,43 @@ def create_pdws_channelized(recordings, M=None, NumTapsPerBand=12, SNR_THRESHOLD
     return {k: np.asarray(v) for k, v in out.items()}
 
 
+def channelizer_example(rec, duration=5e-3, step_frames=100, numBands=None, NumTapsPerBand=12, taps=None):
+    """The math of matlab/channelizer_example.m:18-61 (the surf / VideoWriter part is the caller's) as a generator of
+    frames (f_MHz, t_s, zeroCenterOut):
+
+        iq = iq'                                   conjugate transpose (:23)
+        channelizer = dsp.Channelizer(fs*1e-6)     1 MHz bins (:29-31)
+        for ii = 1 : 100*numBands : length(iq)     windows of 5 ms, stepped by 100 frames (:33-34,50-55)
+            out = abs(channelizer(iq(ii : ii+samples-1)))   ONE stateful object: the FIR history of the previous --
+                                                            overlapping -- window carries into the next call (:56)
+            zeroCenterOut = fftshift(out, 2)       (:58)
+            f = (fc - centerFrequencies(channelizer, fs))*1e-6;  t = ii/fs + (0:rows-1)*numBands/fs   (:60-61)
+
+    The conjugate is not applied to the raw integers (-32768 has no int16 negative): for real taps
+    channelizer(conj(x))[:, k] = conj(channelizer(x)[:, (M-k) mod M]), so abs() of the conjugated input is abs() of the
+    recording's own channels in mirrored order.  That is exact in real arithmetic; in fp32 the two differ by rounding
+    only (tested against the oracle fed the conjugated samples)."""
+    if not isinstance(rec, IqRecording):
+        rec = read_iq(rec)
+    M = int(numBands) if numBands else int(round(rec.fs * 1e-6))                     # :29
+    samples = int(round(duration * rec.fs))                                            # :34
+    ch = Channelizer(M, NumTapsPerBand=NumTapsPerBand, taps=taps)                      # :31
+    try:
+        f = (rec.fc - ch.centerFrequencies(rec.fs)) * 1e-6                             # :60
+        mirror = (-np.arange(M)) % M
+        iq = np.ascontiguousarray(rec.iq)
+        for ii in range(1, iq.shape[0] + 1, step_frames * M):                          # :50 (ii is 1-based as in the script)
+            start, stop = ii, ii + samples - 1                                         # :52-53
+            if stop > iq.shape[0]:                                                     # :55
+                continue
+            out = np.abs(ch(iq[start - 1:stop], rec.bitWidth))[:, mirror]              # :56 (with :23 folded in)
+            zeroCenterOut = np.fft.fftshift(out, axes=1)                               # :58
+            t = ii / rec.fs + np.arange(out.shape[0]) * M / rec.fs                     # :61
+            yield f, t, zeroCenterOut
+    finally:
+        ch.close()
+
+
 def create_pdws(recordings, SNR_THRESHOLD=18.0, TRAILING_EDGE_THRESHOLD=3.0):
     """matlab/create_pdws.m as a function: the wideband (un-channelized) extractor.  The raw stream is
     normalised (:29-32) by a one-channel identity "channelizer" (K1 alone) and fed to the same PDW
@@ -454,5 +491,5 @@ def spectrogram_my_iq(rec):
     return {"power": np.abs(s) ** 2, "f_hz": f + rec.fc, "t_s": t}
 
 
-__all__ = ["PdwTable", "IqRecording", "read_iq", "write_iq", "design_prototype", "Channelizer", "unpack_ptr",
+__all__ = ["PdwTable", "channelizer_example", "IqRecording", "read_iq", "write_iq", "design_prototype", "Channelizer", "unpack_ptr",
            "create_pdws_channelized", "create_pdws", "predict_event", "event_peak_time", "next_event_time", "stft", "spectrogram_my_iq", "ChannelizerError"]

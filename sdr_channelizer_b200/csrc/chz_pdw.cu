@@ -908,6 +908,30 @@ int chz_pdw_shard_thresholds(chz_t* h, const chz_pdw_params_t* params) {
   return pdw_thresholds(h, params, true);
 }
 
+int chz_pdw_shard_set_noise_floor(chz_t* h, const chz_pdw_params_t* params, const double* noise_floor) {
+  if (!h || !params || !noise_floor) return CHZ_EINVAL;
+  CHZ_CUDA(cudaSetDevice(h->device));
+  const int rc = pdw_buffers(h);
+  if (rc) return rc;
+  const uint32_t M = h->M;
+  double scale, scale_lo;
+  threshold_scales(params, &scale, &scale_lo);
+  std::vector<Thr> thr(M);
+  for (uint32_t k = 0; k < M; k++) {     // the same bracketing as thresholds_of() on the device
+    const double tl = noise_floor[k] * scale, tt = noise_floor[k] * scale_lo;
+    float ge = (float)tl, le = (float)tt;
+    if ((double)ge < tl) ge = std::nextafterf(ge, INFINITY);
+    if ((double)le > tt) le = std::nextafterf(le, -INFINITY);
+    thr[k].ge = ge; thr[k].le = le;
+  }
+  h->noise_floor.assign(noise_floor, noise_floor + M);
+  h->pdws.clear();
+  CHZ_CUDA(cudaMemcpyAsync(h->pdw_thr.p, thr.data(), sizeof(Thr) * M, cudaMemcpyHostToDevice, h->stream));
+  CHZ_CUDA(cudaMemcpyAsync(h->pdw_nf.p, noise_floor, sizeof(double) * M, cudaMemcpyHostToDevice, h->stream));
+  CHZ_CUDA(cudaStreamSynchronize(h->stream));
+  return CHZ_OK;
+}
+
 int chz_pdw_shard_exit_state_dev(chz_t* h, const chz_cf32* y_dev, uint64_t nrows, uint8_t* code) {
   if (!h || !code || (!y_dev && nrows)) return CHZ_EINVAL;
   if (h->noise_floor.size() != h->M) return CHZ_ESTATE;

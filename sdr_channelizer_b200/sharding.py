@@ -161,6 +161,16 @@ class PdwShard:
         from . import _lib
         _lib.check(_lib.lib().chz_pdw_shard_thresholds(self.ch.handle, C.byref(self.params)), "chz_pdw_shard_thresholds")
 
+    def set_noise_floor(self, nf):
+        """Skip the median passes: thresholds from a noise floor the caller supplies (chz_pdw_shard_set_noise_floor)."""
+        import ctypes as C
+        import numpy as np
+        from . import _lib
+        nf = np.ascontiguousarray(nf, dtype=np.float64)
+        assert nf.shape == (self.M,)
+        _lib.check(_lib.lib().chz_pdw_shard_set_noise_floor(self.ch.handle, C.byref(self.params), nf.ctypes.data_as(C.c_void_p)),
+                   "chz_pdw_shard_set_noise_floor")
+
     def noise_floor(self):
         import ctypes as C
         import numpy as np

@@ -396,3 +396,59 @@ def test_stft_of_spectrogram_script(orc, tmp_path):
     sp = pkg.spectrogram_my_iq(path)
     assert sp["power"].shape == (768, nseg) and np.allclose(sp["power"], np.abs(ref) ** 2, rtol=1e-4, atol=1e-9 * np.max(np.abs(ref)) ** 2)
     assert sp["f_hz"][384] == 1.0e9
+
+
+# ---- R7 centerFrequencies and the channelizer_example.m script ---------------------------------------------
+@pytest.mark.parametrize("M", [8, 56, 7, 1, 64, 255])
+def test_center_frequencies_product(orc, M):
+    """centerFrequencies(channelizer, fs) as the scripts use it, against the shifted columns
+    (create_pdws_channelized.m:42,60,80; channelizer_example.m:60): chz_channel_freq per natural channel and the
+    Python mirror's centerFrequencies against the oracle, even and odd M."""
+    _torch()
+    fs = 56e6
+    taps = np.ones(M, np.float32) / M
+    ch = pkg.Channelizer(M, taps=taps)
+    ref = orc.center_frequencies(M, fs)                              # ascending, shifted column order
+    got = ch.centerFrequencies(fs)
+    assert got.shape == (M,) and np.allclose(got, ref, rtol=0, atol=1e-6)
+    assert np.all(np.diff(got) > 0) or M == 1
+    nat = np.array([pkg.lib().chz_channel_freq(ch.handle, k, fs) for k in range(M)])
+    for k in range(M):                                               # natural channel k sits in shifted column (k + M//2) % M (:60)
+        assert abs(nat[k] - ref[(k + M // 2) % M]) <= 1e-6
+    assert nat[0] == 0.0 and np.isnan(pkg.lib().chz_channel_freq(ch.handle, M, fs))
+    ch.close()
+
+
+def test_channelizer_example_script(orc, tmp_path):
+    """matlab/channelizer_example.m:18-61: conjugated input (:23), ONE stateful channelizer fed overlapping 5 ms windows
+    stepped by 100 frames (:50-56), abs, fftshift (:58), axes (:60-61) -- against the oracle run on the conjugated
+    samples with the FIR history each call inherits from the window before it."""
+    _torch()
+    fs, fc, M, P = 8e6, 915e6, 8, 12
+    n = 64_000
+    x = synth.tones_complex(n, M, seed=5, centres=(1, 3, 6), amps=(0.4, 0.2, 0.1), off=(2.3, 0.15))
+    iq = np.stack([np.clip(np.rint(x.real * 2047), -2048, 2047), np.clip(np.rint(x.imag * 2047), -2048, 2047)], axis=1).astype(np.int16)
+    path = str(tmp_path / "demo.iq")
+    pkg.write_iq(path, iq, fs=fs, fc=fc, bitWidth=12, sampleStartTime=5.0)
+    taps = pkg.design_prototype(M, P)
+    frames = list(pkg.channelizer_example(path, taps=taps))
+    samples, step, L = int(5e-3 * fs), 100 * M, M * P
+    starts = [ii for ii in range(1, n + 1, step) if ii + samples - 1 <= n]
+    assert len(frames) == len(starts) >= 20
+    xc = np.conj(orc.unpack(iq, 12))                                 # :18-23
+    h = taps.astype(np.float64)
+    prev = np.zeros(0, dtype=np.complex128)
+    for (f, t, z), ii in zip(frames, starts):
+        win = xc[ii - 1:ii - 1 + samples]
+        tail = prev[-(L // M + 1) * M:]                              # whole frames covering the L-1 samples of FIR history
+        ref = np.abs(orc.channelize(np.concatenate([tail, win]), M, h))[len(tail) // M:]
+        ref = np.fft.fftshift(ref, axes=1)                           # :58
+        assert z.shape == ref.shape == (samples // M, M)
+        assert synth.rel_rms(z, ref) <= TOL
+        assert np.allclose(f, (fc - orc.center_frequencies(M, fs)) * 1e-6)             # :60
+        assert np.allclose(t, ii / fs + np.arange(samples // M) * M / fs)              # :61
+        prev = win
+    # a tone at +3 fs/M in the recording shows up at -3 fs/M after the conjugate, i.e. at f = fc + 3 MHz on the script's axis
+    z = frames[-1][2]
+    col = int(np.argmax(z.mean(axis=0)))
+    assert abs(frames[-1][0][col] - (fc * 1e-6 + 1.0)) < 1e-9        # strongest tone: centre 1 -> -1 MHz offset -> f = fc + 1

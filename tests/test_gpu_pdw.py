@@ -424,3 +424,37 @@ def test_sharded_pdws_hysteresis_across_boundaries():
         for recs, nfs in _sharded_on_one_gpu(y, bounds, 1e6, **kw):
             _same_records(recs, whole)
             assert np.array_equal(nfs, nf)
+
+
+@pytest.mark.parametrize("M,seed", [(256, 100), (64, 102)])
+def test_detector_on_the_oracles_thresholds(orc, M, seed):
+    """the GPU takes its noise floor from fp32 |y| of fp32 channels, the oracle from doubles.  Feeding
+    the GPU detector the ORACLE's floor (chz_pdw_shard_set_noise_floor) separates the two error sources: with the same
+    thresholds on the same fp32 channel matrix every edge must fall on the same row (0 rows of tolerance) -- and with
+    its own floor the GPU must reproduce the oracle's floor to fp32 accuracy and the same pulses."""
+    torch = _torch()
+    from sdr_channelizer_b200 import sharding
+    n = M * 9000
+    iq, bw, fs = synth.pulsed_int16(n, M=M, seed=seed)
+    taps = pkg.design_prototype(M, 16)
+    ch = pkg.Channelizer(M, taps=taps)
+    ch.set_stream(torch.cuda.current_stream().cuda_stream)
+    d_in = torch.from_numpy(iq).cuda()
+    rows = n // M
+    y = torch.empty((rows, M), dtype=torch.complex64, device="cuda")
+    ch.process_ptr(d_in.data_ptr(), n, bw, y.data_ptr(), rows)
+    torch.cuda.synchronize()
+    y_host = y.cpu().numpy()
+    orecs, onf = orc.pdws(y_host.astype(np.complex128), M, fc_hz=1e9, fs_sps=fs, t0=2.0)   # oracle on the GPU's own fp32 channels
+    assert len(orecs) >= 3
+    sh = sharding.PdwShard(ch, y.data_ptr(), rows, 0, rows, fs, 1e9, 2.0)
+    sh.set_noise_floor(onf)                                                               # oracle thresholds injected
+    ev = sh.detect(np.zeros(M, np.uint8))
+    pulses = sharding.pair_events(ev, M)
+    assert [(p.channel_natural, p.toa_row, p.end_row) for p in pulses] == [(r.channel_natural, r.toa_row, r.end_row) for r in orecs]
+    recs = [pkg.Pdw.from_buffer_copy(b) for b in sh.records(pulses)]
+    _compare(recs, orecs, fs / M, tol_rows=0)
+    own, nf = ch.pdws_ptr(y.data_ptr(), rows, fs, 1e9, 2.0)                               # the GPU's own median
+    assert np.allclose(nf, onf, rtol=3e-7)
+    _compare(own, orecs, fs / M, tol_rows=0)
+    ch.close()
