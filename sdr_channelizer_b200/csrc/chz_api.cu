@@ -211,6 +211,7 @@ static int ensure_taps(::chz* h, uint32_t bw) {
 // One launch (or FIR + FFT pair) over `nsamp` new device-resident samples; updates the stream state.
 static int run_chunk(::chz* h, const void* iq_dev, uint64_t nsamp, uint32_t bw, float2* out_dev,
                      uint64_t* nrows_out, cudaStream_t st) {
+  NvtxRange nvtx_range("chz:channelize");
   const bool in16 = bw > 8;
   const size_t bps = in16 ? 4 : 2;
   const uint64_t rows_new = (h->consumed + nsamp) / h->D - h->rows_done;
@@ -665,6 +666,7 @@ int chz_process(chz_t* h, const void* iq, uint64_t nsamp, uint32_t bit_width, ch
   if (out && need > out_cap_rows) return CHZ_ECAPACITY;
   if (!out && !h->retain && need) return CHZ_EINVAL;
   CHZ_CUDA(cudaSetDevice(h->device));
+  NvtxRange nvtx_range("chz:process(host buffers)");
   h->bit_width = bit_width;
   const size_t bps = bit_width > 8 ? 4 : 2;
   const uint64_t D = h->D, M = h->M;

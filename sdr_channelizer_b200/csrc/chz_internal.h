@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "channelizer.h"
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost a few ns when no tool is attached
 
 namespace chzi {
 
@@ -24,6 +25,14 @@ void set_cuda_error(cudaError_t e, const char* what, const char* file, int line)
 }  // namespace chzi
 
 namespace chzi {
+// NVTX range per stage: "chz:channelize", "chz:pdw:median", "chz:pdw:detect", "chz:pdw:stats", ...
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 // Device scratch that lives with the handle and only ever grows: cudaMalloc/cudaFree on every call
 // cost up to tens of milliseconds on a busy driver (measured), far more than the PDW kernels.
 struct Scratch {

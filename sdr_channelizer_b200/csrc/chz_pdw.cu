@@ -581,6 +581,7 @@ static int pdw_thresholds(::chz* h, const chz_pdw_params_t* prm, bool fetch) {
 // noise floor rides along in front of the same synchronisation.
 static int pdw_detect(::chz* h, const float2* y, uint64_t nrows, uint64_t row_offset, const uint8_t* entry_host,
                       std::vector<unsigned long long>& ev, bool nf_fetch) {
+  NvtxRange nvtx_range("chz:pdw:detect(events)");
   const int M = (int)h->M;
   cudaStream_t st = h->stream;
   ev.clear();
@@ -704,6 +705,7 @@ static int pdw_records(::chz* h, const chz_pdw_params_t* prm, const float2* y, u
                        const chz_pulse_t* pulses, size_t n, chz_pdw_t* out) {
   if (n == 0) return CHZ_OK;
   if (h->noise_floor.size() != h->M) return CHZ_ESTATE;
+  NvtxRange nvtx_range("chz:pdw:stats");
   cudaStream_t st = h->stream;
   std::vector<PulseIn> pin(n);
   for (size_t i = 0; i < n; i++) {
@@ -751,10 +753,13 @@ static int pdw_extract_fast(::chz* h, const chz_pdw_params_t* prm, const float2*
   cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   auto mark = [&](int i) { if (gtrace) { if (!tev[i]) cudaEventCreate(&tev[i]); cudaEventRecord(tev[i], st); } };
   mark(0);
-  for (int pass = 0; pass < 3; pass++) {
-    if ((rc = pdw_hist_pass(h, y, nrows, pass))) return rc;
-    if (pass < 2 && (rc = pdw_select_pass(h, pass, nrows))) return rc;
-    if (pass == 0) mark(1);
+  {
+    NvtxRange nvtx_median("chz:pdw:median");
+    for (int pass = 0; pass < 3; pass++) {
+      if ((rc = pdw_hist_pass(h, y, nrows, pass))) return rc;
+      if (pass < 2 && (rc = pdw_select_pass(h, pass, nrows))) return rc;
+      if (pass == 0) mark(1);
+    }
   }
   static const int chunk_env = std::getenv("CHZ_PDW_CHUNK_ROWS") ? std::atoi(std::getenv("CHZ_PDW_CHUNK_ROWS")) : 0;   // tuning aid (multiple of 16)
   const int chunk_rows = chunk_env > 0 ? chunk_env : 64;
@@ -764,6 +769,7 @@ static int pdw_extract_fast(::chz* h, const chz_pdw_params_t* prm, const float2*
   const long long blocks = (warps + 7) / 8;
   CHZ_CUDA(h->pdw_ev.reserve((size_t)nchunks * M * sizeof(uint2)));       // chunk summaries (the event list is not used here)
   uint2* d_summ = (uint2*)h->pdw_ev.p;
+  NvtxRange nvtx_range("chz:pdw:detect+stats");
   const int kbug = prm->reproduce_phase_bug ? (int)((0 + (M + 1) / 2) % M) : -1;   // natural channel of shifted column 1 (:114)
   bool selected = false;
   for (;;) {
@@ -827,6 +833,7 @@ static int pdw_extract_fast(::chz* h, const chz_pdw_params_t* prm, const float2*
 }
 
 int pdw_extract(::chz* h, const chz_pdw_params_t* prm, const float2* y, uint64_t nrows) {
+  NvtxRange nvtx_range("chz:pdws");
   const int M = (int)h->M;
   // CHZ_PDW_TRACE=1: host wall-clock of each stage on stderr (debug aid)
   static const bool trace = std::getenv("CHZ_PDW_TRACE") != nullptr;

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
           for (int q = 0; q < 8; q++) v[q] = row[q * 130];
           dft8(v);
           #pragma unroll
-          for (int q = 1; q < 8; q++) v[q] = cmul_p(v[q], tw0[q - 1]);
+          for (int q = 1; q < 8; q++) v[q] = cmul(v[q], tw0[q - 1]);
           #pragma unroll
           for (int q = 0; q < 8; q++) row[q * 130] = v[q];
         }
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
           for (int q = 0; q < 8; q++) v[q] = row[q * 16];
           dft8(v);
           #pragma unroll
-          for (int q = 1; q < 8; q++) v[q] = cmul_p(v[q], tw1s[(q - 1) * 16 + j1]);
+          for (int q = 1; q < 8; q++) v[q] = cmul(v[q], tw1s[(q - 1) * 16 + j1]);
           #pragma unroll
           for (int q = 0; q < 8; q++) row[q * 16] = v[q];
         }
