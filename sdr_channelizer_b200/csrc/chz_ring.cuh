@@ -243,35 +243,37 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
       // ---- FFT, decimation in frequency, in place: 8 (stride 128) x 8 (stride 16) x 16 (contiguous) ----
       {   // pass 0: z_{k0}[j] = W_M^{j k0} sum_q u[j + 128 q] W_8^{q k0}  ->  position 128 k0 + j
         const int j = t & 127, rr = t >> 7;
+        // both butterflies of the thread are loaded before either is computed: twice the loads in flight per warp
+        // (4 warps per scheduler is all the latency hiding this kernel has)
+        float2* row0 = tile + rr * TS + j;
+        float2* row1 = row0 + 4 * TS;
+        float2 v[8], w[8];
         #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          float2* row = tile + (rr + 4 * h) * TS + j;
-          float2 v[8];
-          #pragma unroll
-          for (int q = 0; q < 8; q++) v[q] = row[q * 130];
-          dft8(v);
-          #pragma unroll
-          for (int q = 1; q < 8; q++) v[q] = cmul(v[q], tw0[q - 1]);
-          #pragma unroll
-          for (int q = 0; q < 8; q++) row[q * 130] = v[q];
-        }
+        for (int q = 0; q < 8; q++) { v[q] = row0[q * 130]; w[q] = row1[q * 130]; }
+        dft8(v);
+        dft8(w);
+        #pragma unroll
+        for (int q = 1; q < 8; q++) { v[q] = cmul(v[q], tw0[q - 1]); w[q] = cmul(w[q], tw0[q - 1]); }
+        #pragma unroll
+        for (int q = 0; q < 8; q++) { row0[q * 130] = v[q]; row1[q * 130] = w[q]; }
       }
       // the rest of the FFT is local to a pair of rows: rows rr and rr + 4 belong to the four warps t >> 7
       asm volatile("bar.sync %0, 128;" ::"r"((t >> 7) + 1) : "memory");
       {   // pass 1 inside block k0: w_{k1}[j1] = W_128^{j1 k1} sum_q z[j1 + 16 q] W_8^{q k1}  ->  position 128 k0 + 16 k1 + j1
         const int j1 = t & 15, kb = (t >> 4) & 7, rr = t >> 7;
+        float2* row0 = tile + rr * TS + kb * 130 + j1;
+        float2* row1 = row0 + 4 * TS;
+        float2 v[8], w[8], tw[7];
         #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          float2* row = tile + (rr + 4 * h) * TS + kb * 130 + j1;
-          float2 v[8];
-          #pragma unroll
-          for (int q = 0; q < 8; q++) v[q] = row[q * 16];
-          dft8(v);
-          #pragma unroll
-          for (int q = 1; q < 8; q++) v[q] = cmul(v[q], tw1s[(q - 1) * 16 + j1]);
-          #pragma unroll
-          for (int q = 0; q < 8; q++) row[q * 16] = v[q];
-        }
+        for (int q = 0; q < 8; q++) { v[q] = row0[q * 16]; w[q] = row1[q * 16]; }
+        #pragma unroll
+        for (int q = 1; q < 8; q++) tw[q - 1] = tw1s[(q - 1) * 16 + j1];
+        dft8(v);
+        dft8(w);
+        #pragma unroll
+        for (int q = 1; q < 8; q++) { v[q] = cmul(v[q], tw[q - 1]); w[q] = cmul(w[q], tw[q - 1]); }
+        #pragma unroll
+        for (int q = 0; q < 8; q++) { row0[q * 16] = v[q]; row1[q * 16] = w[q]; }
       }
       asm volatile("bar.sync %0, 128;" ::"r"((t >> 7) + 1) : "memory");
       const int row_i = (t >> 7) + 4 * ((t >> 6) & 1), b = t & 63;
