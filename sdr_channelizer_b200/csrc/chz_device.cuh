@@ -178,6 +178,18 @@ template <int M> struct GroupThreads { static constexpr int value = M < 32 ? M :
 //   M >= 128 (first radix 16): pad every 16, rows 8 apart for M = 128, irrelevant above
 template <int M> struct PadShift { static constexpr int value = (M == 32 || M == 64 || M == 56) ? 3 : 4; };
 template <int M> __device__ __forceinline__ int padi(int i) { return i + (i >> PadShift<M>::value); }
+// Layout of the tile the FIRST pass reads (the one the FIR threads, or a staging copy, write with one lane per
+// branch).  With a pad every 8 elements the 16 lanes of a half-warp store to slots {0..7, 9..16}: slot 16 falls on
+// the banks of slot 0, so every FIR store costs two wavefronts per half-warp instead of one (ncu on M = 64: 38.4 M of
+// 192 M shared wavefronts).  The first pass does not need that pad: it reads BPR consecutive elements per row and
+// RowStride puts consecutive rows half (M = 64, 56) or a quarter (M = 32) of a 128-byte bank window apart, so plain
+// rows are conflict free for the stores and for the reads.  Measured on B200: M = 32 84.0 -> 85.2 %, M = 56 73.7 ->
+// 74.4 % of the HBM roofline; at M = 64 the conflicts drop from 23 % to 6 % of the wavefronts and the LSU data pipe
+// from 82 % to 70 % busy, but the kernel gets 3.5 % SLOWER at 16 taps per band (13 M more instructions after
+// re-scheduling around its 128-register limit; unchanged at 12 taps) -- the LSU pipe was not what bounds it
+// (profiles/r02g_*).  So the plain layout is used for 32 and 56 only.
+template <int M> struct FirstPassPlain { static constexpr bool value = (M == 32 || M == 56); };
+template <int M> __device__ __forceinline__ int padi_first(int i) { return FirstPassPlain<M>::value ? i : padi<M>(i); }
 template <int M> struct RowStride {
   static constexpr int value = M == 32 ? 36 : (M == 64 ? 72 : (M == 56 ? 72 : M + M / 16 + (M < 16 ? 1 : 0)));
 };
@@ -206,7 +218,7 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, fl
     const float2* s = src + row * S;
     float2 v[R];
     #pragma unroll
-    for (int q = 0; q < R; q++) v[q] = s[padi<M>(j + q * BPR)];
+    for (int q = 0; q < R; q++) v[q] = s[NS == 1 ? padi_first<M>(j + q * BPR) : padi<M>(j + q * BPR)];
     const int k = j % NS;               // NS is a compile-time constant (a power of two except in Plan<560>)
     if (NS > 1) {
       // twiddle table layout (host: build_twiddles): per pass, entry (q-1)*NS + k holds

@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(NT) k_fft_rows(const float2* u, float2* y,   /
     __syncthreads();
     for (int e = threadIdx.x; e < ROWS * M; e += NT) {
       const int row = e / M, i = e - row * M;
-      buf0[row * S + padi<M>(i)] = row < vrows ? u[(r0 + row) * M + i] : make_float2(0.f, 0.f);
+      buf0[row * S + padi_first<M>(i)] = row < vrows ? u[(r0 + row) * M + i] : make_float2(0.f, 0.f);
     }
     __syncthreads();
     fft_tile_to_global<M, ROWS, NT, false>(buf0, buf1, tw, nullptr, threadIdx.x, y + r0 * M, (long long)M, 0, vrows,
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 
   for (long long s = (long long)blockIdx.x * G + g; s < nspans; s += (long long)gridDim.x * G) {
     const Span sp = make_span(prm, s);
     if (sp.count <= 0) continue;                      // the whole group takes the same branch
-    const int r = padi<M>((p - sp.shift + M) % M);
+    const int r = padi_first<M>((p - sp.shift + M) % M);
     float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
     fir_span<P, IN16, M, 0>(prm, sp, p, [&](int ii, long long i, float2 v) {
       if (branch) buf0[(ii % RT) * S + r] = v;

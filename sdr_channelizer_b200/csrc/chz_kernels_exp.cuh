@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256, 3) k_chan_ws(ChanParams prm) {
     for (long long s = gg; s < nspans; s += gstride) {
       const Span sp = make_span(prm, s);
       if (sp.count <= 0) continue;
-      const int r = padi<M>((p - sp.shift + M) % M);
+      const int r = padi_first<M>((p - sp.shift + M) % M);
       fir_span<P, IN16, M, 2>(prm, sp, p, [&](int ii, long long, float2 v) {
         const unsigned b = tile % WS_NB, n = tile / WS_NB;
         if (ii == 0 && n > 0) mbar_wait(&empty[b], (n - 1) & 1);       // the FFT warps are done with this buffer
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256, 2) k_chan_dsm(ChanParams prm) {
   for (long long s = cid; s < nspans; s += ncl) {      // cluster-uniform loop
     const Span sp = make_span(prm, s);
     if (sp.count <= 0) continue;
-    const unsigned pos = (unsigned)padi<M>((p - sp.shift + M) % M) * (unsigned)sizeof(float2);
+    const unsigned pos = (unsigned)padi_first<M>((p - sp.shift + M) % M) * (unsigned)sizeof(float2);
     float2* gout = prm.out + (sp.m0 - prm.row_base) * (long long)M;
     fir_span<P, IN16, M, 0>(prm, sp, p, [&](int ii, long long i, float2 v) {
       const unsigned sl = tile & 1;
