@@ -28,6 +28,22 @@ static int launch_ring(::chz* h, const ChanParams& prm, cudaStream_t st) {
   if (const char* e = std::getenv("CHZ_RING_DBG")) rp.dbg = std::atoi(e);
   // one persistent CTA per SM; a CTA's run starts with a 16-frame warm-up, so short calls use fewer CTAs
   long long grid = std::min<long long>(h->sm_count, std::max<long long>(1, rp.nsteps / h->ring_min_steps));
+#ifdef CHZ_EXPERIMENTS
+  static const int variant = std::getenv("CHZ_RING_VARIANT") ? std::atoi(std::getenv("CHZ_RING_VARIANT")) : 0;   // tuning aid
+  if (variant == 1) {      // 1024 threads, one branch each
+    auto kern1k = ring::k_chan_ring1k<P, IN16, UNPACK>;
+    static thread_local bool attr1k_dev[kMaxDev] = {false};
+    bool& attr1k = attr1k_dev[h->device % kMaxDev];
+    if (!attr1k) {
+      CHZ_CUDA(cudaFuncSetAttribute(kern1k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+      attr1k = true;
+    }
+    kern1k<<<(unsigned)grid, ring::kNT1k, SM::TOTAL, st>>>(prm, rp);
+    h->launches++;
+    CHZ_CUDA(cudaGetLastError());
+    return CHZ_OK;
+  }
+#endif
   kern<<<(unsigned)grid, ring::kNT, SM::TOTAL, st>>>(prm, rp);
   h->launches++;
   CHZ_CUDA(cudaGetLastError());

@@ -167,6 +167,8 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
     const long long a0 = rp.a_lo + k * kR;
     const int s_mid = s_old == 2 ? 0 : s_old + 1, s_new = s_mid == 2 ? 0 : s_mid + 1;
     if (pending) { mbar_wait(bar, parity); parity ^= 1; }
+    else __syncthreads();       // the newest slot was filled by every thread's bounds-checked copy: after the FIR's barrier only
+                                // row-group barriers follow, so a CTA-wide one is needed before those writes are read
     const unsigned sb0 = ring_s + s_old * SLOTB, sb1 = ring_s + s_mid * SLOTB, sb2 = ring_s + s_new * SLOTB;
 
     for (int ph = 0; ph < os; ph++, buf ^= 1) {
@@ -298,6 +300,177 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
     s_old = s_mid;
   }
 }
+
+
+#ifdef CHZ_EXPERIMENTS
+// ---- 1024-thread variant: one branch per thread (make EXPERIMENTS=1, CHZ_RING_VARIANT=1) --------------------------
+// MEASURED SLOWER than the 512-thread kernel: 225 against 273 GS/s critically sampled, 115.7 against 136.0 GS/s on
+// configs[2] (profiles/r02h_ring_1024_threads_ab.jsonl).  Twice the warps do not buy latency hiding here: per output
+// the addressing, the ring reads (LDS.32 per branch instead of LDS.64 per pair) and the re-read taps cost more issue
+// slots than the shorter stalls give back.  Kept as a record of the experiment.
+// Same ring, same tiles, same arithmetic per row (identical results), but 32 warps instead of 16: the 512-thread kernel
+// alternates between an FMA-bound FIR and shared-memory-bound FFT passes with 4 warps per scheduler, i.e. with little
+// latency hiding inside either.  64 registers per thread suffice because nothing stays resident between the phases: a
+// thread owns ONE ring column (taps of its branch are re-read from L2 for every phase: 64 KB per CTA and phase, the
+// pass-0 twiddles likewise), every radix-8 pass has exactly one butterfly per thread, and the last (radix-16) pass
+// occupies the lower half of every row's warps while the upper half already filters the next phase into the other
+// tile buffer.  A thread's single column also removes the branch-0 fix-up: its frame offset delta is per thread.
+constexpr int kNT1k = 1024;
+
+template <int P, bool IN16, int UNPACK>
+__global__ void __launch_bounds__(kNT1k, 1) k_chan_ring1k(ChanParams prm, RingParams rp) {
+  typedef Smem<IN16> SM;
+  typedef typename RawT<IN16>::type raw_t;
+  constexpr int M = kM, ROWB = SM::ROWB, SLOTB = SM::SLOTB, TS = kTileStride;
+  constexpr int J0 = 16 - P;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2* tiles = (float2*)(smem + SM::OFF_TILE);
+  float2* tw1s = (float2*)(smem + SM::OFF_TW1);
+  const unsigned ring_s = smem_u32(smem), bar = smem_u32(smem + SM::OFF_BAR);
+  const int t = threadIdx.x;
+  const int os = prm.os, D = prm.D;
+  const long long k0 = rp.nsteps * blockIdx.x / gridDim.x, k1 = rp.nsteps * (blockIdx.x + 1) / gridDim.x;
+  if (k0 >= k1) return;
+
+  const int c = t;                                  // ring column of phase 0; branch p0 = (M - c) mod M
+  const int p0 = (M - c) & (M - 1);
+  if (t < 7 * 16) tw1s[t] = __ldg(rp.twn + ((((t & 15) * ((t >> 4) + 1)) << 3) & (M - 1)));   // W_128^{j1 k} at [k-1][j1]
+  if (t == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long in_end = prm.in_base + prm.n_in;
+  const bool aligned = ((((unsigned long long)prm.in) - (unsigned long long)prm.in_base * sizeof(raw_t)) & 15ull) == 0;
+  const raw_t* __restrict__ inp = (const raw_t*)prm.in - prm.in_base;
+  unsigned parity = 0;
+  bool pending = false;
+  auto load_slot = [&](long long a, int s) -> bool {
+    const long long lo = a * M, hi = lo + (long long)kR * M;
+    if (aligned && lo >= prm.in_base && hi <= in_end) {
+      if (t == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, SLOTB);
+        bulk_g2s(ring_s + s * SLOTB, inp + lo, SLOTB, bar);
+      }
+      return true;
+    }
+    raw_t* dst = (raw_t*)(smem + s * SLOTB);
+    #pragma unroll 4
+    for (int e = t; e < kR * M; e += kNT1k) dst[e] = (raw_t)load_raw<IN16>(prm, lo + e);
+    return false;
+  };
+  const long long a_start = rp.a_lo + k0 * kR;
+  if (load_slot(a_start - 2 * kR, 0)) { mbar_wait(bar, parity); parity ^= 1; }
+  __syncthreads();
+  if (load_slot(a_start - kR, 1)) { mbar_wait(bar, parity); parity ^= 1; }
+  __syncthreads();
+  pending = load_slot(a_start, 2);
+  __syncthreads();
+
+  int s_old = 0, buf = 0;
+  for (long long k = k0; k < k1; k++) {
+    const long long a0 = rp.a_lo + k * kR;
+    const int s_mid = s_old == 2 ? 0 : s_old + 1, s_new = s_mid == 2 ? 0 : s_mid + 1;
+    if (pending) { mbar_wait(bar, parity); parity ^= 1; }
+    else __syncthreads();       // the newest slot was filled by every thread's bounds-checked copy: after the FIR's barrier only
+                                // row-group barriers follow, so a CTA-wide one is needed before those writes are read
+    const unsigned sb0 = ring_s + s_old * SLOTB, sb1 = ring_s + s_mid * SLOTB, sb2 = ring_s + s_new * SLOTB;
+
+    for (int ph = 0; ph < os; ph++, buf ^= 1) {
+      float2* tile = tiles + buf * (kR * TS);
+      {
+        // ---- FIR: 8 rows of branch p0.  Row m = os*a + ph reads x[a M + ph D - q M - p0] = frame (a - q - 1 + delta),
+        // column cc:  ph = 0: cc = c, delta = (c == 0);  ph = 1: cc = (c + D) mod M, delta = (p0 <= D)
+        const int cc = ph ? ((c + D) & (M - 1)) : c;
+        const bool dl = ph ? (p0 <= D) : (c == 0);
+        const unsigned cb = (unsigned)cc * sizeof(raw_t);
+        const unsigned dcol = cb + (dl ? ROWB : 0);
+        const unsigned r0b = sb0 + dcol, r1b = sb1 + dcol, r2b = sb2 + dcol;
+        const unsigned e0 = dl ? sb1 + cb : sb0 + 7 * ROWB + cb;
+        const unsigned e1 = dl ? sb2 + cb : sb1 + 7 * ROWB + cb;
+        float h[P];
+        #pragma unroll
+        for (int q = 0; q < P; q++) h[q] = __ldg(prm.taps + q * M + p0);
+        float2 acc[kR];
+        #pragma unroll
+        for (int r = 0; r < kR; r++) acc[r] = make_float2(0.f, 0.f);
+        #pragma unroll
+        for (int ii = 0; ii < P + kR - 1; ii++) {
+          const int j = ii + J0;
+          const unsigned addr = (j & 7) == 7 ? (j < 8 ? e0 : e1) : ((j < 8 ? r0b : (j < 16 ? r1b : r2b)) + (j & 7) * ROWB);
+          uint32_t w;
+          if (IN16) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
+          else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w) : "r"(addr));
+          const float2 x = unpack<IN16, UNPACK>(w);
+          #pragma unroll
+          for (int r = 0; r < kR; r++) {
+            const int q = r + P - 1 - ii;
+            if (q >= 0 && q < P) acc[r] = __ffma2_rn(make_float2(h[q], h[q]), x, acc[r]);
+          }
+        }
+        const int pos = tpad((p0 - (ph ? D : 0)) & (M - 1));
+        #pragma unroll
+        for (int r = 0; r < kR; r++) tile[r * TS + pos] = acc[r];
+      }
+      __syncthreads();                               // the tile is complete, nobody reads the ring any more
+      if (ph == os - 1) pending = (k + 1 < k1) ? load_slot(a0 + kR, s_old) : false;
+
+      const int row = t >> 7, tg = t & 127;          // from here on a row belongs to the four warps t >> 7
+      {   // pass 0: z_{k0}[j] = W_M^{j k0} sum_q u[j + 128 q] W_8^{q k0}  ->  position 128 k0 + j
+        float2 tw[7];
+        #pragma unroll
+        for (int q = 1; q < 8; q++) tw[q - 1] = __ldg(rp.twn + ((tg * q) & (M - 1)));
+        float2* rp0 = tile + row * TS + tg;
+        float2 v[8];
+        #pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = rp0[q * 130];
+        dft8(v);
+        #pragma unroll
+        for (int q = 1; q < 8; q++) v[q] = cmul(v[q], tw[q - 1]);
+        #pragma unroll
+        for (int q = 0; q < 8; q++) rp0[q * 130] = v[q];
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(row + 1) : "memory");
+      {   // pass 1 inside block k0
+        const int j1 = tg & 15, kb = tg >> 4;
+        float2* rp1 = tile + row * TS + kb * 130 + j1;
+        float2 v[8], tw[7];
+        #pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = rp1[q * 16];
+        #pragma unroll
+        for (int q = 1; q < 8; q++) tw[q - 1] = tw1s[(q - 1) * 16 + j1];
+        dft8(v);
+        #pragma unroll
+        for (int q = 1; q < 8; q++) v[q] = cmul(v[q], tw[q - 1]);
+        #pragma unroll
+        for (int q = 0; q < 8; q++) rp1[q * 16] = v[q];
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(row + 1) : "memory");
+      if (tg < 64) {   // pass 2: the lower two warps of the row; the upper two go on to the next phase's FIR
+        const int b = tg, kb = b & 7, kc = b >> 3;
+        const float4* src = (const float4*)(tile + row * TS + kb * 130 + kc * 16);
+        float2 v[16];
+        #pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const float4 f = src[q];
+          v[2 * q] = make_float2(f.x, f.y); v[2 * q + 1] = make_float2(f.z, f.w);
+        }
+        dft16(v);
+        const long long m = (a0 + row) * os + ph;
+        if (m >= prm.row_base && m < prm.row_base + prm.nrows) {
+          float2* g = prm.out + (m - prm.row_base) * (long long)M + b;
+          #pragma unroll
+          for (int q = 0; q < 16; q++) g[q * 64] = v[q];
+        }
+      }
+    }
+    s_old = s_mid;
+  }
+}
+
+#endif  // CHZ_EXPERIMENTS
 
 }  // namespace ring
 }  // namespace chzi
