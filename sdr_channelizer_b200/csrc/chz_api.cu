@@ -32,7 +32,8 @@ LaunchPlan plan_spans(const ::chz* h, long long nrows, int P, int groups_per_blo
   const long long total_groups = max_blocks * groups_per_block;
   long long sr = (rows_per_phase + total_groups * 4 - 1) / (total_groups * 4);
   sr = (sr + P - 1) / P * P;
-  const long long lo = 4LL * P, hi = (4096LL / P) * P;
+  static const long long span_cap = std::getenv("CHZ_SPAN_CAP") ? std::atoll(std::getenv("CHZ_SPAN_CAP")) : 4096;   // tuning aid
+  const long long lo = 4LL * P, hi = (span_cap / P) * P;
   if (sr < lo) sr = lo;
   if (sr > hi) sr = hi;
   lp.span_rows = (int)sr;
@@ -520,6 +521,7 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
     CHZ_TRY(cudaMalloc(&h->d_twn, sizeof(float2) * M));
     CHZ_TRY(cudaMemcpy(h->d_twn, twn.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
   }
+  if (const char* e = std::getenv("CHZ_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(e));   // tuning aid: 32 / 64 / 128
   if (const char* e = std::getenv("CHZ_RING_UNPACK")) h->ring_unpack = std::atoi(e);          // tuning aids
   if (const char* e = std::getenv("CHZ_RING_MIN_STEPS")) { const int v = std::atoi(e); if (v > 0) h->ring_min_steps = v; }
   CHZ_TRY(cudaMalloc(&h->d_tw, sizeof(float2) * M));
