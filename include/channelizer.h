@@ -234,8 +234,8 @@ int chz_pdw_shard_select(chz_t* h, int pass, uint64_t total_rows);
 int chz_pdw_shard_thresholds(chz_t* h, const chz_pdw_params_t* params);
 /* Instead of the three histogram/select passes and chz_pdw_shard_thresholds: take the per-channel noise floor
  * (natural order, M doubles) from the caller and derive the thresholds from it exactly as above.  For callers that
- * already know the floor (a calibration run, an earlier dwell) and for tests that feed the detector the double-
- * precision oracle's median, to tell threshold error from detection error. */
+ * already know the floor (a calibration run, an earlier dwell) and for tests that feed the detector a double-
+ * precision median, to tell threshold error from detection error. */
 int chz_pdw_shard_set_noise_floor(chz_t* h, const chz_pdw_params_t* params, const double* noise_floor);
 /* code[k] (host, M bytes, natural channels): state of the edge FSM after this shard's last row as a
  * function of the state it is entered with: 0 inactive, 1 active, 2 = entry state, 3 = entry state toggled. */

@@ -347,7 +347,7 @@ def channelizer_example(rec, duration=5e-3, step_frames=100, numBands=None, NumT
     The conjugate is not applied to the raw integers (-32768 has no int16 negative): for real taps
     channelizer(conj(x))[:, k] = conj(channelizer(x)[:, (M-k) mod M]), so abs() of the conjugated input is abs() of the
     recording's own channels in mirrored order.  That is exact in real arithmetic; in fp32 the two differ by rounding
-    only (tested against the oracle fed the conjugated samples)."""
+    only (tested against a double-precision evaluation of the conjugated samples)."""
     if not isinstance(rec, IqRecording):
         rec = read_iq(rec)
     M = int(numBands) if numBands else int(round(rec.fs * 1e-6))                     # :29
