@@ -191,6 +191,10 @@ __global__ void __launch_bounds__(128, 4) k_fir(ChanParams prm, float2* __restri
   const int groups = 128 / bpb;                    // spans handled side by side in one block
   const int bb = blockIdx.x % nbb, g = threadIdx.x / bpb;
   if (g >= groups) return;                         // 128 is not a multiple of bpb (M = 56: 16 spare threads)
+  // Branch p reads x[mD - p]: with lanes on branches 32w .. 32w+31 a warp's 128 bytes start 4 bytes past a line boundary
+  // (5 sectors per load, and the L1's sector promotion on top: at configs[3] size k_fir reads 1.67x the recording from
+  // DRAM).  Moving every thread one branch up, (p + 1) mod M, line-aligns the loads but misaligns the 8-byte stores of
+  // u instead: measured 143 against 185 GS/s on configs[3] -- rejected.
   const int p = bb * bpb + threadIdx.x % bpb;
   const long long nspans = prm.spans_per_phase * prm.os;
   const long long sstride = (long long)(gridDim.x / nbb) * groups;
