@@ -443,6 +443,8 @@ __global__ void __launch_bounds__(FusedCfg<M, P>::NT, FusedCfg<M, P>::NT <= 256 
   // non-power-of-two M: the spare lanes of the last warp shadow branch M-1 through the FIR (same control
   // flow, so they meet every barrier) without storing, and take their share of the FFT butterflies
   const bool branch = MG == M || t < M;
+  // (thread t on branch (t + 1) mod M would make a warp's 32 samples x[mD - p] one aligned line; measured: no gain at
+  // M = 64 (435.6 against 441.0 GS/s), a loss at M = 128 -- the loads' extra sector is not what bounds this kernel)
   const int p = branch ? t : M - 1;
   float2* buf0 = smem + M + (size_t)g * CF::GSTRIDE;   // [RT][S]
   float2* buf1 = buf0 + RT * S;
