@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
           #pragma unroll
           for (int r = 0; r < kR; r++) {
             const int q = r + P - 1 - ii;
-            if (q >= 0 && q < P) acc1[r] = __ffma2_rn(make_float2(h1[q], h1[q]), xb, acc1[r]);
+            if (q >= 0 && q < P) acc1[r] = __ffma2_rn(make_float2(h1[q], h1[q]), xb, acc1[r]);   // (one branch packed, one scalar: 243 against 273 GS/s)
           }
         }
         const int shift = ph ? D : 0;
