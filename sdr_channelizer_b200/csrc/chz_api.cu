@@ -523,6 +523,8 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
   }
   if (const char* e = std::getenv("CHZ_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(e));   // tuning aid: 32 / 64 / 128
   if (const char* e = std::getenv("CHZ_RING_UNPACK")) h->ring_unpack = std::atoi(e);          // tuning aids
+  if (const char* e = std::getenv("CHZ_RING_VARIANT")) h->ring_variant = std::atoi(e);
+  if (const char* e = std::getenv("CHZ_RING_DBG")) h->ring_dbg = std::atoi(e);
   if (const char* e = std::getenv("CHZ_RING_MIN_STEPS")) { const int v = std::atoi(e); if (v > 0) h->ring_min_steps = v; }
   CHZ_TRY(cudaMalloc(&h->d_tw, sizeof(float2) * M));
   CHZ_TRY(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));

@@ -61,7 +61,7 @@ struct chz {
   float* d_taps[17] = {nullptr};        // per bit width: taps * 2^-(bw-1), uploaded on first use
   float2* d_tw = nullptr;               // inter-pass twiddles of the Stockham plan (per-pass layout, chz_create)
   float2* d_twn = nullptr;              // plain table e^{+j 2 pi i / M}, i < M (ring kernel)
-  int ring_min_steps = 4, ring_unpack = 1;   // ring kernel: 8-frame steps per CTA at least; unpack policy (CHZ_RING_UNPACK)
+  int ring_min_steps = 4, ring_unpack = 1, ring_variant = 0, ring_dbg = 0;   // ring kernel: 8-frame steps per CTA at least; tuning aids (CHZ_RING_* environment, read at chz_create)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};

@@ -194,7 +194,10 @@ __global__ void __launch_bounds__(128, 4) k_fir(ChanParams prm, float2* __restri
   // Branch p reads x[mD - p]: with lanes on branches 32w .. 32w+31 a warp's 128 bytes start 4 bytes past a line boundary
   // (5 sectors per load, and the L1's sector promotion on top: at configs[3] size k_fir reads 1.67x the recording from
   // DRAM).  Moving every thread one branch up, (p + 1) mod M, line-aligns the loads but misaligns the 8-byte stores of
-  // u instead: measured 143 against 185 GS/s on configs[3] -- rejected.
+  // u instead: measured 143 against 185 GS/s on configs[3] -- rejected.  Storing the row ROTATED by one element as
+  // well (aligned loads, aligned stores) and reading it back one element later in the FFT kernel moves the misalignment
+  // to the 8-byte reads of a kernel that already runs at 92 % of the DRAM peak: 186.9 against 210.1 GS/s at 280 M samples,
+  // 182.5 against 186.4 at full size -- rejected too.
   const int p = bb * bpb + threadIdx.x % bpb;
   const long long nspans = prm.spans_per_phase * prm.os;
   const long long sstride = (long long)(gridDim.x / nbb) * groups;

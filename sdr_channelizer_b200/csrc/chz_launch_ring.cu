@@ -1,53 +1,49 @@
-// Launcher of the large-M fused ring kernel (k_chan_ring, chz_ring.cuh): M = 1024, P in {8, 12, 16}.
+// Launcher of the large-M fused ring kernel (k_chan_ring_ws, chz_ring.cuh): M = 1024, P in {8, 12, 16}.
 #include <algorithm>
 #include <cstdlib>
 
 #include "chz_internal.h"
 #include "chz_ring.cuh"
+#ifdef CHZ_EXPERIMENTS
+#include "chz_ring_exp.cuh"
+#endif
 #include "chz_launch.h"
 
 namespace chzi {
 
+template <typename K>
+static int launch_one(::chz* h, K kern, bool& attr, long long grid, int threads, int smem, const ChanParams& prm,
+                      const ring::RingParams& rp, cudaStream_t st) {
+  if (!attr) {
+    CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  kern<<<(unsigned)grid, threads, smem, st>>>(prm, rp);
+  h->launches++;
+  CHZ_CUDA(cudaGetLastError());
+  return CHZ_OK;
+}
+
 template <int P, bool IN16, int UNPACK>
 static int launch_ring(::chz* h, const ChanParams& prm, cudaStream_t st) {
   typedef ring::Smem<IN16> SM;
-  auto kern = ring::k_chan_ring<P, IN16, UNPACK>;
-  static thread_local bool attr_dev[kMaxDev] = {false};
-  bool& attr = attr_dev[h->device % kMaxDev];
-  if (!attr) {
-    CHZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    attr = true;
-  }
   ring::RingParams rp;
   const long long os = prm.os;
   rp.a_lo = prm.row_base / os;
   const long long a_hi = (prm.row_base + prm.nrows - 1) / os + 1;
   rp.nsteps = (a_hi - rp.a_lo + ring::kR - 1) / ring::kR;
   rp.twn = h->d_twn;
-  rp.dbg = 0;
-  if (const char* e = std::getenv("CHZ_RING_DBG")) rp.dbg = std::atoi(e);
+  rp.dbg = h->ring_dbg;
   // one persistent CTA per SM; a CTA's run starts with a 16-frame warm-up, so short calls use fewer CTAs
-  long long grid = std::min<long long>(h->sm_count, std::max<long long>(1, rp.nsteps / h->ring_min_steps));
+  const long long grid = std::min<long long>(h->sm_count, std::max<long long>(1, rp.nsteps / h->ring_min_steps));
+  static thread_local bool attr_dev[3][kMaxDev] = {};
 #ifdef CHZ_EXPERIMENTS
-  static const int variant = std::getenv("CHZ_RING_VARIANT") ? std::atoi(std::getenv("CHZ_RING_VARIANT")) : 0;   // tuning aid
-  if (variant == 1) {      // 1024 threads, one branch each
-    auto kern1k = ring::k_chan_ring1k<P, IN16, UNPACK>;
-    static thread_local bool attr1k_dev[kMaxDev] = {false};
-    bool& attr1k = attr1k_dev[h->device % kMaxDev];
-    if (!attr1k) {
-      CHZ_CUDA(cudaFuncSetAttribute(kern1k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-      attr1k = true;
-    }
-    kern1k<<<(unsigned)grid, ring::kNT1k, SM::TOTAL, st>>>(prm, rp);
-    h->launches++;
-    CHZ_CUDA(cudaGetLastError());
-    return CHZ_OK;
-  }
+  if (h->ring_variant == 1)      // every warp filters, then transforms
+    return launch_one(h, ring::k_chan_ring<P, IN16, UNPACK>, attr_dev[1][h->device % kMaxDev], grid, ring::kNT, SM::TOTAL, prm, rp, st);
+  if (h->ring_variant == 2)      // 1024 threads, one branch each
+    return launch_one(h, ring::k_chan_ring1k<P, IN16, UNPACK>, attr_dev[2][h->device % kMaxDev], grid, ring::kNT1k, SM::TOTAL, prm, rp, st);
 #endif
-  kern<<<(unsigned)grid, ring::kNT, SM::TOTAL, st>>>(prm, rp);
-  h->launches++;
-  CHZ_CUDA(cudaGetLastError());
-  return CHZ_OK;
+  return launch_one(h, ring::k_chan_ring_ws<P, IN16, UNPACK>, attr_dev[0][h->device % kMaxDev], grid, ring::kNT, SM::TOTAL, prm, rp, st);
 }
 
 template <bool IN16, int UNPACK>

@@ -5,12 +5,13 @@
 //
 // One persistent CTA per SM owns a contiguous run of the recording.  On chip it keeps
 //   * a ring of the last 24 raw frames A_a = x[aM, aM+M) (int16 pairs as recorded, 4 KB each), fed by
-//     cp.async.bulk (TMA, mbarrier completion) eight frames at a time while the FFT of the previous eight runs;
-//   * the P taps of two polyphase branches per thread in registers;
-//   * one tile of 8 output rows x M channels (fp32 complex) on which the M-point FFT runs IN PLACE.
-// Per step a thread reads the P+7 raw words of its two branches once from the ring, unpacks them and feeds
-// eight running sums per branch (no re-reads of the recording from L2: DRAM and L2 see every sample once),
-// the CTA then runs a decimation-in-frequency FFT 8 x 8 x 16 whose last pass streams the rows to global memory
+//     cp.async.bulk (TMA, mbarrier completion) eight frames at a time, prefetched into L2 one step ahead;
+//   * the P taps of four polyphase branches per FIR thread in registers;
+//   * two tiles of 8 output rows x M channels (fp32 complex): the FIR warps fill one while the FFT warps
+//     transform the other IN PLACE.
+// Per step a FIR thread reads the P+7 raw words of each of its branches once from the ring, unpacks them and feeds
+// eight running sums per branch (no re-reads of the recording from L2: DRAM and L2 see every sample once);
+// the FFT warps run a decimation-in-frequency FFT 8 x 8 x 16 whose last pass streams the rows to global memory
 // with the lanes across channels (whole 256-byte runs per store).  2x oversampling = the same step run twice
 // per ring advance: the odd rows read the ring half a frame later and rotate the branches by M/2.
 #pragma once
@@ -20,7 +21,7 @@ namespace chzi {
 namespace ring {
 
 constexpr int kM = 1024;        // channels = branches per CTA
-constexpr int kNT = 512;        // threads: two adjacent branches each
+constexpr int kNT = 512;        // threads: 8 FIR warps (four branches per thread) + 8 FFT warps
 constexpr int kR = 8;           // output rows per tile = frames per ring slot
 constexpr int kSlots = 3;       // ring = 3 slots of 8 frames: rows a0-16 .. a0+7 of the step at a0
 constexpr int kTileStride = kM + 2 * (kM / 128) - 2;   // float2 per tile row: 2 pad elements after each 128-block but the last (see pass 2)
@@ -85,12 +86,36 @@ __device__ __forceinline__ float2 unpack(uint32_t raw) {
 // quarter-warp that read 16-byte pieces of eight different 128-blocks in pass 2 hit distinct banks
 __device__ __forceinline__ int tpad(int pos) { return pos + ((pos >> 7) << 1); }
 
+// ---- the kernel: FIR warps and FFT warps over the two tile buffers -------------------------------------------------
+// A kernel in which every warp alternates between the FIR (FMA pipe / register-file bandwidth bound) and the FFT
+// passes (shared-memory bound) leaves each pipe idle while the other works: that was the first round-2 kernel
+// (k_chan_ring in chz_ring_exp.cuh: 273 / 136 GS/s critical / 2x).  Here warps 0-7 only filter (tile n+1) while
+// warps 8-15 only transform (tile n): a FIR thread carries the taps of FOUR branches (two column pairs, filtered one
+// after the other with the same 16 accumulators) and raises its register budget with setmaxnreg, an FFT thread takes
+// four radix-8 butterflies per pass (two at a time) and lowers it.  Hand-off per tile buffer through named barriers in
+// the producer/consumer pattern (bar.arrive by one role, bar.sync by the other); the ring and its TMA copies belong to
+// the FIR warps alone.  Same arithmetic per row as k_chan_ring: bit-identical results.
+// Measured (profiles/r02j_ring_ws_ab.jsonl): 310 / 162 GS/s critical / 2x at P = 16 (57.5 % / 50.1 % of HBM),
+// 340 GS/s at P = 12, 362 GS/s at P = 8.
+//
+// Register split between the roles (setmaxnreg; the sum over 8 + 8 warps must stay within 65 536): the FIR code needs
+// 134 registers at P = 16.  A/B over 128/128, 136/120, 144/112, 152/104, 160/96: all within +-3 % (instruction
+// scheduling differences); 136/120 is best at P = 16 and 8, 152/104 at P = 12.
+template <int P> struct RoleRegs {
+  static constexpr int FIR = P == 12 ? 152 : 136, FFT = P == 12 ? 104 : 120;
+  static_assert(8 * 32 * (FIR + FFT) <= 65536, "register file");
+};
+
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 template <int P, bool IN16, int UNPACK>
-__global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams rp) {
+__global__ void __launch_bounds__(kNT, 1) k_chan_ring_ws(ChanParams prm, RingParams rp) {
   typedef Smem<IN16> SM;
   typedef typename RawT<IN16>::type raw_t;
   constexpr int M = kM, ROWB = SM::ROWB, SLOTB = SM::SLOTB, TS = kTileStride;
-  constexpr int J0 = 16 - P;                      // first ring row (relative to a0-16) a delta = 0 thread reads
+  constexpr int J0 = 16 - P;
+  constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_FIR = 5, BAR_FFT = 6;   // named barriers: full[2], empty[2], FIR group, FFT row groups [2]
   extern __shared__ __align__(128) unsigned char smem[];
   float2* tiles = (float2*)(smem + SM::OFF_TILE);
   float* h0s = (float*)(smem + SM::OFF_H0);
@@ -98,134 +123,141 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
   const unsigned ring_s = smem_u32(smem), bar = smem_u32(smem + SM::OFF_BAR);
   const int t = threadIdx.x;
   const int os = prm.os, D = prm.D;
-
-  // ---- this CTA's run of steps ----
   const long long k0 = rp.nsteps * blockIdx.x / gridDim.x, k1 = rp.nsteps * (blockIdx.x + 1) / gridDim.x;
   if (k0 >= k1) return;
-
-  // ---- persistent per-thread state: taps of branches 2t+1 and (2t+2) mod M, twiddles of passes 0 and 1 ----
-  const int b1 = 2 * t + 1, b2 = (2 * t + 2) & (M - 1);
-  float h1[P], h2[P];
-  #pragma unroll
-  for (int q = 0; q < P; q++) { h1[q] = __ldg(prm.taps + q * M + b1); h2[q] = __ldg(prm.taps + q * M + b2); }
   if (t < P) h0s[t] = __ldg(prm.taps + t * M);
-  float2 tw0[7];
-  #pragma unroll
-  for (int k = 1; k < 8; k++) tw0[k - 1] = __ldg(rp.twn + (((t & 127) * k) & (M - 1)));   // W_M^{j k}, j = t mod 128
-  if (t < 7 * 16) tw1s[t] = __ldg(rp.twn + ((((t & 15) * ((t >> 4) + 1)) << 3) & (M - 1)));   // W_128^{j1 k} at [k-1][j1]
+  if (t < 7 * 16) tw1s[t] = __ldg(rp.twn + ((((t & 15) * ((t >> 4) + 1)) << 3) & (M - 1)));
   if (t == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  const long long nphases = (k1 - k0) * os;
 
-  const long long in_end = prm.in_base + prm.n_in;
-  // bulk copies need 16-byte aligned global addresses: frame starts are multiples of M samples from in_base
-  const bool aligned = ((((unsigned long long)prm.in) - (unsigned long long)prm.in_base * sizeof(raw_t)) & 15ull) == 0;
-  const raw_t* __restrict__ inp = (const raw_t*)prm.in - prm.in_base;   // inp[idx], idx in [in_base, in_end)
-  unsigned parity = 0;
-  bool pending = false;                           // a bulk copy into the newest slot is in flight
-
-  // frames [a, a+8) -> ring slot s.  Whole slot inside this call's input and aligned: one bulk copy issued by
-  // thread 0 (the caller waits on the mbarrier before reading); otherwise every thread copies with bounds
-  // checks (history buffer, zeros before the stream start and past the data) and the caller synchronises.
-  auto load_slot = [&](long long a, int s) -> bool {
-    const long long lo = a * M, hi = lo + (long long)kR * M;
-    if (rp.dbg & 4) return false;
-    if (aligned && lo >= prm.in_base && hi <= in_end) {
-      if (t == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, SLOTB);
-        bulk_g2s(ring_s + s * SLOTB, inp + lo, SLOTB, bar);
+  if (t < 256) {
+    // =========================== FIR warps ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RoleRegs<P>::FIR));
+    const int f = t;
+    float hA1[P], hA2[P], hB1[P], hB2[P];           // taps of the column pairs u = f and u = f + 256
+    {
+      const int a1 = 2 * f + 1, a2 = 2 * f + 2, b1 = 2 * (f + 256) + 1, b2 = (2 * (f + 256) + 2) & (M - 1);
+      #pragma unroll
+      for (int q = 0; q < P; q++) {
+        hA1[q] = __ldg(prm.taps + q * M + a1); hA2[q] = __ldg(prm.taps + q * M + a2);
+        hB1[q] = __ldg(prm.taps + q * M + b1); hB2[q] = __ldg(prm.taps + q * M + b2);
       }
-      return true;
     }
-    raw_t* dst = (raw_t*)(smem + s * SLOTB);
-    #pragma unroll 4
-    for (int e = t; e < kR * M; e += kNT) dst[e] = (raw_t)load_raw<IN16>(prm, lo + e);
-    return false;
-  };
-
-  const long long a_start = rp.a_lo + k0 * kR;
-  // warm-up: the 16 frames before the first step.  One bulk copy at a time on the single mbarrier, and a
-  // CTA barrier after every wait so that no thread can still be polling phase n when phase n + 1 completes.
-  if (load_slot(a_start - 2 * kR, 0)) { mbar_wait(bar, parity); parity ^= 1; }
-  __syncthreads();
-  if (load_slot(a_start - kR, 1)) { mbar_wait(bar, parity); parity ^= 1; }
-  __syncthreads();
-  pending = load_slot(a_start, 2);
-
-  __syncthreads();                                 // ring writes of a slow-path warm-up are visible
-
-  // Per phase: FIR -> tile[buf] | CTA barrier | pass 0 | pass 1 | pass 2 + global stores -> straight into the next
-  // phase's FIR, which writes the OTHER tile buffer.  Rows are independent in the FFT, so its passes are separated by
-  // named barriers of the four warps that own a pair of rows only; one CTA-wide barrier remains per eight rows, and a
-  // warp that is done with its rows starts filtering while others still stream theirs out.
-  int s_old = 0;                                   // slot of frames a0-16 .. a0-9
-  int buf = 0;
-  for (long long k = k0; k < k1; k++) {
-    const long long a0 = rp.a_lo + k * kR;
-    const int s_mid = s_old == 2 ? 0 : s_old + 1, s_new = s_mid == 2 ? 0 : s_mid + 1;
-    if (pending) { mbar_wait(bar, parity); parity ^= 1; }
-    else __syncthreads();       // the newest slot was filled by every thread's bounds-checked copy: after the FIR's barrier only
-                                // row-group barriers follow, so a CTA-wide one is needed before those writes are read
-    const unsigned sb0 = ring_s + s_old * SLOTB, sb1 = ring_s + s_mid * SLOTB, sb2 = ring_s + s_new * SLOTB;
-
-    for (int ph = 0; ph < os; ph++, buf ^= 1) {
-      float2* tile = tiles + buf * (kR * TS);
-      // ---- FIR: 8 rows x 2 branches per thread ----
-      // Row m = os*a + ph, branch p reads x[a M + ph D - q M - p] = frame (a - q - 1 + delta), column cl:
-      //   ph = 0: cl = M - p, delta = 0 (p >= 1);  ph = 1: p <= D: cl = D - p, delta = 1;  p > D: cl = M + D - p, delta = 0.
-      // The pair (2t+2, 2t+1) is the 8-byte aligned pair of columns (cl, cl + 1).  Branch 0 (thread 511's
-      // first element) is the one column whose delta differs from its neighbour's: fixed up below.
-      const bool lowhalf = ph && t < D / 2;
-      const int cl = ph ? (lowhalf ? D - 2 * t - 2 : M + D - 2 * t - 2) : M - 2 * t - 2;
-      const unsigned dcol = (unsigned)cl * sizeof(raw_t) + (lowhalf ? ROWB : 0);
-      const unsigned r0b = sb0 + dcol, r1b = sb1 + dcol, r2b = sb2 + dcol;
-      const unsigned e0 = lowhalf ? sb1 + cl * (unsigned)sizeof(raw_t) : sb0 + 7 * ROWB + cl * (unsigned)sizeof(raw_t);
-      const unsigned e1 = lowhalf ? sb2 + cl * (unsigned)sizeof(raw_t) : sb1 + 7 * ROWB + cl * (unsigned)sizeof(raw_t);
-      if (!(rp.dbg & 2)) {
-        float2 acc1[kR], acc2[kR];
-        #pragma unroll
-        for (int r = 0; r < kR; r++) { acc1[r] = make_float2(0.f, 0.f); acc2[r] = make_float2(0.f, 0.f); }
-        #pragma unroll
-        for (int ii = 0; ii < P + kR - 1; ii++) {
-          const int j = ii + J0;                       // ring row (before delta), compile time
-          const unsigned addr = (j & 7) == 7 ? (j < 8 ? e0 : e1) : ((j < 8 ? r0b : (j < 16 ? r1b : r2b)) + (j & 7) * ROWB);
-          uint32_t wa, wb;                             // columns cl (branch 2t+2) and cl+1 (branch 2t+1)
-          if (IN16) {
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wa), "=r"(wb) : "r"(addr));
-          } else {
-            uint32_t w;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
-            wa = w & 0xffffu; wb = w >> 16;
-          }
-          const float2 xa = unpack<IN16, UNPACK>(wa), xb = unpack<IN16, UNPACK>(wb);
-          #pragma unroll
-          for (int r = 0; r < kR; r++) {
-            const int q = r + P - 1 - ii;
-            if (q >= 0 && q < P) acc2[r] = __ffma2_rn(make_float2(h2[q], h2[q]), xa, acc2[r]);
-          }
-          #pragma unroll
-          for (int r = 0; r < kR; r++) {
-            const int q = r + P - 1 - ii;
-            if (q >= 0 && q < P) acc1[r] = __ffma2_rn(make_float2(h1[q], h1[q]), xb, acc1[r]);   // (one branch packed, one scalar: 243 against 273 GS/s)
-          }
+    const long long in_end = prm.in_base + prm.n_in;
+    const bool aligned = ((((unsigned long long)prm.in) - (unsigned long long)prm.in_base * sizeof(raw_t)) & 15ull) == 0;
+    const raw_t* __restrict__ inp = (const raw_t*)prm.in - prm.in_base;
+    unsigned parity = 0;
+    bool pending = false;
+    auto load_slot = [&](long long a, int s) -> bool {      // FIR warps only
+      const long long lo = a * M, hi = lo + (long long)kR * M;
+      if (aligned && lo >= prm.in_base && hi <= in_end && !(rp.dbg & 4)) {
+        if (f == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(bar, SLOTB);
+          bulk_g2s(ring_s + s * SLOTB, inp + lo, SLOTB, bar);
         }
+        return true;
+      }
+      raw_t* dst = (raw_t*)(smem + s * SLOTB);
+      if (!(rp.dbg & 4)) {
+        #pragma unroll 4
+        for (int e = f; e < kR * M; e += 256) dst[e] = (raw_t)load_raw<IN16>(prm, lo + e);
+      }
+      return false;
+    };
+    // the copy of step k+1's frames can only be issued when step k is through (all three slots are live until then);
+    // asking L2 for them a step ahead takes the HBM latency out of that copy (+4 % measured; two steps ahead: no
+    // further gain; refilling the slot in two column halves as each falls dead: -5 %, the extra barrier and the
+    // sixteen 2 KB copies cost more than the wait they remove)
+    auto prefetch_slot = [&](long long a) {
+      const long long lo = a * M, hi = lo + (long long)kR * M;
+      if (f == 0 && aligned && lo >= prm.in_base && hi <= in_end)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(inp + lo), "r"(SLOTB) : "memory");
+    };
+    const long long a_start = rp.a_lo + k0 * kR;
+    if (load_slot(a_start - 2 * kR, 0)) { mbar_wait(bar, parity); parity ^= 1; }
+    bar_sync(BAR_FIR, 256);
+    if (load_slot(a_start - kR, 1)) { mbar_wait(bar, parity); parity ^= 1; }
+    bar_sync(BAR_FIR, 256);
+    pending = load_slot(a_start, 2);
+
+    int s_old = 0;
+    long long n = 0;                                 // phase counter: tile buffer n & 1
+    for (long long k = k0; k < k1; k++) {
+      const int s_mid = s_old == 2 ? 0 : s_old + 1, s_new = s_mid == 2 ? 0 : s_mid + 1;
+      if (pending) { mbar_wait(bar, parity); parity ^= 1; }
+      else bar_sync(BAR_FIR, 256);                   // bounds-checked copy by the FIR threads: visible after their barrier
+      if (k + 1 < k1) prefetch_slot(rp.a_lo + (k + 1) * kR);
+      const unsigned sb0 = ring_s + s_old * SLOTB, sb1 = ring_s + s_mid * SLOTB, sb2 = ring_s + s_new * SLOTB;
+      for (int ph = 0; ph < os; ph++, n++) {
+        const int buf = (int)(n & 1);
+        float2* tile = tiles + buf * (kR * TS);
+        if (n >= 2) bar_sync(BAR_EMPTY + buf, kNT);  // the FFT warps have drained this buffer (tile n - 2)
         const int shift = ph ? D : 0;
-        const int pos1 = tpad((b1 - shift) & (M - 1)), pos2 = tpad((b2 - shift) & (M - 1));
-        #pragma unroll
-        for (int r = 0; r < kR; r++) { tile[r * TS + pos1] = acc1[r]; tile[r * TS + pos2] = acc2[r]; }
-        if (t >= kNT - 32) {
-          // branch 0: u_0[m] = sum_q h[qM] x[a M + ph D - q M] = frame (a - q), column ph*D: rows 16 + r - q of the ring
+        // one column pair: 8 rows x branches (2u+2, 2u+1)
+        auto fir_pair = [&](int u, const float (&h1)[P], const float (&h2)[P]) {
+          const bool lowhalf = ph && u < D / 2;
+          const int cl = ph ? (lowhalf ? D - 2 * u - 2 : M + D - 2 * u - 2) : M - 2 * u - 2;
+          const unsigned dcol = (unsigned)cl * sizeof(raw_t) + (lowhalf ? ROWB : 0);
+          const unsigned r0b = sb0 + dcol, r1b = sb1 + dcol, r2b = sb2 + dcol;
+          const unsigned e0 = lowhalf ? sb1 + cl * (unsigned)sizeof(raw_t) : sb0 + 7 * ROWB + cl * (unsigned)sizeof(raw_t);
+          const unsigned e1 = lowhalf ? sb2 + cl * (unsigned)sizeof(raw_t) : sb1 + 7 * ROWB + cl * (unsigned)sizeof(raw_t);
+          float2 acc1[kR], acc2[kR];
+          #pragma unroll
+          for (int r = 0; r < kR; r++) { acc1[r] = make_float2(0.f, 0.f); acc2[r] = make_float2(0.f, 0.f); }
+          #pragma unroll
+          for (int ii = 0; ii < P + kR - 1; ii++) {
+            const int j = ii + J0;
+            const unsigned addr = (j & 7) == 7 ? (j < 8 ? e0 : e1) : ((j < 8 ? r0b : (j < 16 ? r1b : r2b)) + (j & 7) * ROWB);
+            uint32_t wa, wb;
+            if (IN16) {
+              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wa), "=r"(wb) : "r"(addr));
+            } else {
+              uint32_t w;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
+              wa = w & 0xffffu; wb = w >> 16;
+            }
+            const float2 xa = unpack<IN16, UNPACK>(wa), xb = unpack<IN16, UNPACK>(wb);
+            #pragma unroll
+            for (int r = 0; r < kR; r++) {
+              const int q = r + P - 1 - ii;
+              if (q >= 0 && q < P) acc2[r] = __ffma2_rn(make_float2(h2[q], h2[q]), xa, acc2[r]);
+            }
+            #pragma unroll
+            for (int r = 0; r < kR; r++) {
+              const int q = r + P - 1 - ii;
+              if (q >= 0 && q < P) acc1[r] = __ffma2_rn(make_float2(h1[q], h1[q]), xb, acc1[r]);
+            }
+          }
+          // A warp storing one branch per lane writes every other element (8 bytes at a 16-byte stride: four
+          // shared-memory wavefronts for 256 bytes).  Every other group of 8 lanes stores its branches in the opposite order, so that
+          // each instruction covers all 16 bank pairs twice: two wavefronts.
+          const int pos1 = tpad((2 * u + 1 - shift) & (M - 1)), pos2 = tpad((2 * u + 2 - shift) & (M - 1));
+          const bool swp = (u & 8) != 0;
+          float2* t1 = tile + (swp ? pos2 : pos1);
+          float2* t2 = tile + (swp ? pos1 : pos2);
+          #pragma unroll
+          for (int r = 0; r < kR; r++) {
+            t1[r * TS] = swp ? acc2[r] : acc1[r];
+            t2[r * TS] = swp ? acc1[r] : acc2[r];
+          }
+        };
+        auto fix_branch0 = [&]() {
+          if (f < 224) return;
+          // branch 0 (second element of pair u = 511, written just above by lane 31 of this warp): its frame offset
+          // differs from its neighbour's, so eight lanes recompute it from frame (a - q), column ph*D
           __syncwarp();
-          const int r = t & 31;
+          const int r = f & 31;
           if (r < kR) {
             float2 acc = make_float2(0.f, 0.f);
             const unsigned c0 = (unsigned)(ph ? D : 0) * sizeof(raw_t);
             #pragma unroll
             for (int q = P - 1; q >= 0; q--) {
-              const int i = 16 + r - q;                 // 1 .. 23
+              const int i = 16 + r - q;
               const unsigned sb = i < 8 ? sb0 : (i < 16 ? sb1 : sb2);
               uint32_t w;
               if (IN16) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sb + (i & 7) * ROWB + c0));
@@ -234,21 +266,38 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
             }
             tile[r * TS + tpad((0 - shift) & (M - 1))] = acc;
           }
+        };
+        if (!(rp.dbg & 2)) {
+          fir_pair(f, hA1, hA2);
+          fir_pair(f + 256, hB1, hB2);
+          fix_branch0();
         }
+        bar_arrive(BAR_FULL + buf, kNT);             // tile n is complete
       }
-      __syncthreads();                               // barrier A: the tile is complete, nobody reads the ring any more
-      // the oldest slot is dead after the last phase's FIR: request the next step's frames into it now, the
-      // copy lands while the FFT passes run
-      if (ph == os - 1) pending = (k + 1 < k1) ? load_slot(a0 + kR, s_old) : false;
-
-      if (rp.dbg & 1) continue;
-      // ---- FFT, decimation in frequency, in place: 8 (stride 128) x 8 (stride 16) x 16 (contiguous) ----
-      {   // pass 0: z_{k0}[j] = W_M^{j k0} sum_q u[j + 128 q] W_8^{q k0}  ->  position 128 k0 + j
-        const int j = t & 127, rr = t >> 7;
-        // both butterflies of the thread are loaded before either is computed: twice the loads in flight per warp
-        // (4 warps per scheduler is all the latency hiding this kernel has)
-        float2* row0 = tile + rr * TS + j;
-        float2* row1 = row0 + 4 * TS;
+      // the oldest ring slot is dead once every FIR warp is through this step: request the next step's frames
+      bar_sync(BAR_FIR, 256);
+      pending = k + 1 < k1 ? load_slot(rp.a_lo + (k + 1) * kR, s_old) : false;
+      s_old = s_mid;
+    }
+  } else {
+    // =========================== FFT warps ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RoleRegs<P>::FFT));
+    const int g = t - 256;
+    const int rr = g >> 7, tg = g & 127;             // rows rr, rr+2, rr+4, rr+6 belong to the 4 warps g >> 7
+    float2 tw0[7];
+    #pragma unroll
+    for (int q = 1; q < 8; q++) tw0[q - 1] = __ldg(rp.twn + ((tg * q) & (M - 1)));
+    for (long long n = 0; n < nphases; n++) {
+      const int buf = (int)(n & 1);
+      float2* tile = tiles + buf * (kR * TS);
+      const long long a0 = rp.a_lo + (k0 + n / os) * kR;
+      const int ph = (int)(n % os);
+      bar_sync(BAR_FULL + buf, kNT);                 // the FIR warps have finished tile n
+      if (rp.dbg & 1) { bar_arrive(BAR_EMPTY + buf, kNT); continue; }
+      #pragma unroll
+      for (int hh = 0; hh < 2; hh++) {               // pass 0: four butterflies per thread, two at a time
+        float2* row0 = tile + (rr + 4 * hh) * TS + tg;
+        float2* row1 = row0 + 2 * TS;
         float2 v[8], w[8];
         #pragma unroll
         for (int q = 0; q < 8; q++) { v[q] = row0[q * 130]; w[q] = row1[q * 130]; }
@@ -259,218 +308,52 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring(ChanParams prm, RingParams
         #pragma unroll
         for (int q = 0; q < 8; q++) { row0[q * 130] = v[q]; row1[q * 130] = w[q]; }
       }
-      // the rest of the FFT is local to a pair of rows: rows rr and rr + 4 belong to the four warps t >> 7
-      asm volatile("bar.sync %0, 128;" ::"r"((t >> 7) + 1) : "memory");
-      {   // pass 1 inside block k0: w_{k1}[j1] = W_128^{j1 k1} sum_q z[j1 + 16 q] W_8^{q k1}  ->  position 128 k0 + 16 k1 + j1
-        const int j1 = t & 15, kb = (t >> 4) & 7, rr = t >> 7;
-        float2* row0 = tile + rr * TS + kb * 130 + j1;
-        float2* row1 = row0 + 4 * TS;
-        float2 v[8], w[8], tw[7];
-        #pragma unroll
-        for (int q = 0; q < 8; q++) { v[q] = row0[q * 16]; w[q] = row1[q * 16]; }
+      bar_sync(BAR_FFT + rr, 128);
+      {
+        const int j1 = tg & 15, kb = tg >> 4;
+        float2 tw[7];
         #pragma unroll
         for (int q = 1; q < 8; q++) tw[q - 1] = tw1s[(q - 1) * 16 + j1];
-        dft8(v);
-        dft8(w);
         #pragma unroll
-        for (int q = 1; q < 8; q++) { v[q] = cmul(v[q], tw[q - 1]); w[q] = cmul(w[q], tw[q - 1]); }
-        #pragma unroll
-        for (int q = 0; q < 8; q++) { row0[q * 16] = v[q]; row1[q * 16] = w[q]; }
+        for (int hh = 0; hh < 2; hh++) {             // pass 1
+          float2* row0 = tile + (rr + 4 * hh) * TS + kb * 130 + j1;
+          float2* row1 = row0 + 2 * TS;
+          float2 v[8], w[8];
+          #pragma unroll
+          for (int q = 0; q < 8; q++) { v[q] = row0[q * 16]; w[q] = row1[q * 16]; }
+          dft8(v);
+          dft8(w);
+          #pragma unroll
+          for (int q = 1; q < 8; q++) { v[q] = cmul(v[q], tw[q - 1]); w[q] = cmul(w[q], tw[q - 1]); }
+          #pragma unroll
+          for (int q = 0; q < 8; q++) { row0[q * 16] = v[q]; row1[q * 16] = w[q]; }
+        }
       }
-      asm volatile("bar.sync %0, 128;" ::"r"((t >> 7) + 1) : "memory");
-      const int row_i = (t >> 7) + 4 * ((t >> 6) & 1), b = t & 63;
-      {   // pass 2: y[k0 + 8 k1 + 64 k2] = sum_{j1} w[j1] W_16^{j1 k2}; lanes run over (k0, k1): 32 consecutive channels per store
+      bar_sync(BAR_FFT + rr, 128);
+      #pragma unroll 1
+      for (int hh = 0; hh < 2; hh++) {               // pass 2: two radix-16 butterflies per thread
+        const int row_i = rr + 2 * ((tg >> 6) & 1) + 4 * hh, b = tg & 63;
         const int kb = b & 7, kc = b >> 3;
         const float4* src = (const float4*)(tile + row_i * TS + kb * 130 + kc * 16);
         float2 v[16];
         #pragma unroll
         for (int q = 0; q < 8; q++) {
-          const float4 f = src[q];
-          v[2 * q] = make_float2(f.x, f.y); v[2 * q + 1] = make_float2(f.z, f.w);
+          const float4 f4 = src[q];
+          v[2 * q] = make_float2(f4.x, f4.y); v[2 * q + 1] = make_float2(f4.z, f4.w);
         }
+        if (hh == 1) bar_arrive(BAR_EMPTY + buf, kNT);   // this thread's last read of the tile is in registers
         dft16(v);
         const long long m = (a0 + row_i) * os + ph;
         if (m >= prm.row_base && m < prm.row_base + prm.nrows) {
-          float2* g = prm.out + (m - prm.row_base) * (long long)M + b;
+          float2* gp = prm.out + (m - prm.row_base) * (long long)M + b;
           #pragma unroll
-          for (int q = 0; q < 16; q++) g[q * 64] = v[q];
+          for (int q = 0; q < 16; q++) gp[q * 64] = v[q];
         }
       }
     }
-    s_old = s_mid;
   }
 }
 
-
-#ifdef CHZ_EXPERIMENTS
-// ---- 1024-thread variant: one branch per thread (make EXPERIMENTS=1, CHZ_RING_VARIANT=1) --------------------------
-// MEASURED SLOWER than the 512-thread kernel: 225 against 273 GS/s critically sampled, 115.7 against 136.0 GS/s on
-// configs[2] (profiles/r02h_ring_1024_threads_ab.jsonl).  Twice the warps do not buy latency hiding here: per output
-// the addressing, the ring reads (LDS.32 per branch instead of LDS.64 per pair) and the re-read taps cost more issue
-// slots than the shorter stalls give back.  Kept as a record of the experiment.
-// Same ring, same tiles, same arithmetic per row (identical results), but 32 warps instead of 16: the 512-thread kernel
-// alternates between an FMA-bound FIR and shared-memory-bound FFT passes with 4 warps per scheduler, i.e. with little
-// latency hiding inside either.  64 registers per thread suffice because nothing stays resident between the phases: a
-// thread owns ONE ring column (taps of its branch are re-read from L2 for every phase: 64 KB per CTA and phase, the
-// pass-0 twiddles likewise), every radix-8 pass has exactly one butterfly per thread, and the last (radix-16) pass
-// occupies the lower half of every row's warps while the upper half already filters the next phase into the other
-// tile buffer.  A thread's single column also removes the branch-0 fix-up: its frame offset delta is per thread.
-constexpr int kNT1k = 1024;
-
-template <int P, bool IN16, int UNPACK>
-__global__ void __launch_bounds__(kNT1k, 1) k_chan_ring1k(ChanParams prm, RingParams rp) {
-  typedef Smem<IN16> SM;
-  typedef typename RawT<IN16>::type raw_t;
-  constexpr int M = kM, ROWB = SM::ROWB, SLOTB = SM::SLOTB, TS = kTileStride;
-  constexpr int J0 = 16 - P;
-  extern __shared__ __align__(128) unsigned char smem[];
-  float2* tiles = (float2*)(smem + SM::OFF_TILE);
-  float2* tw1s = (float2*)(smem + SM::OFF_TW1);
-  const unsigned ring_s = smem_u32(smem), bar = smem_u32(smem + SM::OFF_BAR);
-  const int t = threadIdx.x;
-  const int os = prm.os, D = prm.D;
-  const long long k0 = rp.nsteps * blockIdx.x / gridDim.x, k1 = rp.nsteps * (blockIdx.x + 1) / gridDim.x;
-  if (k0 >= k1) return;
-
-  const int c = t;                                  // ring column of phase 0; branch p0 = (M - c) mod M
-  const int p0 = (M - c) & (M - 1);
-  if (t < 7 * 16) tw1s[t] = __ldg(rp.twn + ((((t & 15) * ((t >> 4) + 1)) << 3) & (M - 1)));   // W_128^{j1 k} at [k-1][j1]
-  if (t == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  const long long in_end = prm.in_base + prm.n_in;
-  const bool aligned = ((((unsigned long long)prm.in) - (unsigned long long)prm.in_base * sizeof(raw_t)) & 15ull) == 0;
-  const raw_t* __restrict__ inp = (const raw_t*)prm.in - prm.in_base;
-  unsigned parity = 0;
-  bool pending = false;
-  auto load_slot = [&](long long a, int s) -> bool {
-    const long long lo = a * M, hi = lo + (long long)kR * M;
-    if (aligned && lo >= prm.in_base && hi <= in_end) {
-      if (t == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, SLOTB);
-        bulk_g2s(ring_s + s * SLOTB, inp + lo, SLOTB, bar);
-      }
-      return true;
-    }
-    raw_t* dst = (raw_t*)(smem + s * SLOTB);
-    #pragma unroll 4
-    for (int e = t; e < kR * M; e += kNT1k) dst[e] = (raw_t)load_raw<IN16>(prm, lo + e);
-    return false;
-  };
-  const long long a_start = rp.a_lo + k0 * kR;
-  if (load_slot(a_start - 2 * kR, 0)) { mbar_wait(bar, parity); parity ^= 1; }
-  __syncthreads();
-  if (load_slot(a_start - kR, 1)) { mbar_wait(bar, parity); parity ^= 1; }
-  __syncthreads();
-  pending = load_slot(a_start, 2);
-  __syncthreads();
-
-  int s_old = 0, buf = 0;
-  for (long long k = k0; k < k1; k++) {
-    const long long a0 = rp.a_lo + k * kR;
-    const int s_mid = s_old == 2 ? 0 : s_old + 1, s_new = s_mid == 2 ? 0 : s_mid + 1;
-    if (pending) { mbar_wait(bar, parity); parity ^= 1; }
-    else __syncthreads();       // the newest slot was filled by every thread's bounds-checked copy: after the FIR's barrier only
-                                // row-group barriers follow, so a CTA-wide one is needed before those writes are read
-    const unsigned sb0 = ring_s + s_old * SLOTB, sb1 = ring_s + s_mid * SLOTB, sb2 = ring_s + s_new * SLOTB;
-
-    for (int ph = 0; ph < os; ph++, buf ^= 1) {
-      float2* tile = tiles + buf * (kR * TS);
-      {
-        // ---- FIR: 8 rows of branch p0.  Row m = os*a + ph reads x[a M + ph D - q M - p0] = frame (a - q - 1 + delta),
-        // column cc:  ph = 0: cc = c, delta = (c == 0);  ph = 1: cc = (c + D) mod M, delta = (p0 <= D)
-        const int cc = ph ? ((c + D) & (M - 1)) : c;
-        const bool dl = ph ? (p0 <= D) : (c == 0);
-        const unsigned cb = (unsigned)cc * sizeof(raw_t);
-        const unsigned dcol = cb + (dl ? ROWB : 0);
-        const unsigned r0b = sb0 + dcol, r1b = sb1 + dcol, r2b = sb2 + dcol;
-        const unsigned e0 = dl ? sb1 + cb : sb0 + 7 * ROWB + cb;
-        const unsigned e1 = dl ? sb2 + cb : sb1 + 7 * ROWB + cb;
-        float h[P];
-        #pragma unroll
-        for (int q = 0; q < P; q++) h[q] = __ldg(prm.taps + q * M + p0);
-        float2 acc[kR];
-        #pragma unroll
-        for (int r = 0; r < kR; r++) acc[r] = make_float2(0.f, 0.f);
-        #pragma unroll
-        for (int ii = 0; ii < P + kR - 1; ii++) {
-          const int j = ii + J0;
-          const unsigned addr = (j & 7) == 7 ? (j < 8 ? e0 : e1) : ((j < 8 ? r0b : (j < 16 ? r1b : r2b)) + (j & 7) * ROWB);
-          uint32_t w;
-          if (IN16) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
-          else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w) : "r"(addr));
-          const float2 x = unpack<IN16, UNPACK>(w);
-          #pragma unroll
-          for (int r = 0; r < kR; r++) {
-            const int q = r + P - 1 - ii;
-            if (q >= 0 && q < P) acc[r] = __ffma2_rn(make_float2(h[q], h[q]), x, acc[r]);
-          }
-        }
-        const int pos = tpad((p0 - (ph ? D : 0)) & (M - 1));
-        #pragma unroll
-        for (int r = 0; r < kR; r++) tile[r * TS + pos] = acc[r];
-      }
-      __syncthreads();                               // the tile is complete, nobody reads the ring any more
-      if (ph == os - 1) pending = (k + 1 < k1) ? load_slot(a0 + kR, s_old) : false;
-
-      const int row = t >> 7, tg = t & 127;          // from here on a row belongs to the four warps t >> 7
-      {   // pass 0: z_{k0}[j] = W_M^{j k0} sum_q u[j + 128 q] W_8^{q k0}  ->  position 128 k0 + j
-        float2 tw[7];
-        #pragma unroll
-        for (int q = 1; q < 8; q++) tw[q - 1] = __ldg(rp.twn + ((tg * q) & (M - 1)));
-        float2* rp0 = tile + row * TS + tg;
-        float2 v[8];
-        #pragma unroll
-        for (int q = 0; q < 8; q++) v[q] = rp0[q * 130];
-        dft8(v);
-        #pragma unroll
-        for (int q = 1; q < 8; q++) v[q] = cmul(v[q], tw[q - 1]);
-        #pragma unroll
-        for (int q = 0; q < 8; q++) rp0[q * 130] = v[q];
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(row + 1) : "memory");
-      {   // pass 1 inside block k0
-        const int j1 = tg & 15, kb = tg >> 4;
-        float2* rp1 = tile + row * TS + kb * 130 + j1;
-        float2 v[8], tw[7];
-        #pragma unroll
-        for (int q = 0; q < 8; q++) v[q] = rp1[q * 16];
-        #pragma unroll
-        for (int q = 1; q < 8; q++) tw[q - 1] = tw1s[(q - 1) * 16 + j1];
-        dft8(v);
-        #pragma unroll
-        for (int q = 1; q < 8; q++) v[q] = cmul(v[q], tw[q - 1]);
-        #pragma unroll
-        for (int q = 0; q < 8; q++) rp1[q * 16] = v[q];
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(row + 1) : "memory");
-      if (tg < 64) {   // pass 2: the lower two warps of the row; the upper two go on to the next phase's FIR
-        const int b = tg, kb = b & 7, kc = b >> 3;
-        const float4* src = (const float4*)(tile + row * TS + kb * 130 + kc * 16);
-        float2 v[16];
-        #pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const float4 f = src[q];
-          v[2 * q] = make_float2(f.x, f.y); v[2 * q + 1] = make_float2(f.z, f.w);
-        }
-        dft16(v);
-        const long long m = (a0 + row) * os + ph;
-        if (m >= prm.row_base && m < prm.row_base + prm.nrows) {
-          float2* g = prm.out + (m - prm.row_base) * (long long)M + b;
-          #pragma unroll
-          for (int q = 0; q < 16; q++) g[q * 64] = v[q];
-        }
-      }
-    }
-    s_old = s_mid;
-  }
-}
-
-#endif  // CHZ_EXPERIMENTS
 
 }  // namespace ring
 }  // namespace chzi

@@ -135,7 +135,7 @@ extern "C" int chz_write_iq(const char* path, const chz_iq_info_t* in, const voi
   put(&in->bit_width, 4);
   if (in->format >= 2) put(&in->spare0, 4);
   const char* strs[4] = {in->board_name, in->serial_number, in->fpga_version, in->fw_version};
-  for (const char* s : strs) { char b[16]; memset(b, 0, 16); strncpy(b, s, 16); put(b, 16); }
+  for (const char* s : strs) { char b[16]; memset(b, 0, 16); memcpy(b, s, strnlen(s, 16)); put(b, 16); }
   put(&in->sample_start_time, 8);
   FILE* fp = fopen(path, "wb");
   if (!fp) return CHZ_EIO;
