@@ -455,21 +455,11 @@ def main():
     ms_per_step = max_over_ranks(total_ms) / args.steps
     value = (n_own * world) / (ms_per_step * 1e-3) / 1e6      # owned samples of all ranks / max time
 
-    # sustained figure: 200 more launches back to back (the board's power management lowers the SM clock after
-    # ~50 ms of this kernel; the timed region above is whatever --steps asked for)
-    sus_n = 200
-    sev = [torch.cuda.Event(enable_timing=True) for _ in range(sus_n + 1)]
-    sev[0].record(stream)
-    for i in range(sus_n):
-        step()
-        sev[i + 1].record(stream)
-    barrier()
-    sus_ms = statistics.mean(sev[i].elapsed_time(sev[i + 1]) for i in range(sus_n // 2, sus_n))
-
     # What a do-nothing kernel with the SAME traffic reaches on this board: K1 alone (int16 pair -> float2: 4 B read,
     # 8 B written per sample) over the same buffers.  The copy peak in MEASURED_PEAKS.json is a 1:1 read:write mix;
     # this path writes twice what it reads, and no kernel we tried moves that mix faster than K1 does
     # (tools/ubench/mixbw.cu: 128-bit variants 4.6-5.1 TB/s, K1 5.6 TB/s, copy 6.5 TB/s).
+    # Measured right after the timed region, before the 200-launch sustained run heats the board.
     same_traffic = None
     if BIT_WIDTH > 8 and OVERSAMPLE == 1:
         nev = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
@@ -481,6 +471,17 @@ def main():
             nev[i + 1].record(stream)
         barrier()
         same_traffic = statistics.mean(nev[i].elapsed_time(nev[i + 1]) for i in range(10))
+
+    # sustained figure: 200 more launches back to back (the board's power management lowers the SM clock after
+    # ~50 ms of this kernel; the timed region above is whatever --steps asked for)
+    sus_n = 200
+    sev = [torch.cuda.Event(enable_timing=True) for _ in range(sus_n + 1)]
+    sev[0].record(stream)
+    for i in range(sus_n):
+        step()
+        sev[i + 1].record(stream)
+    barrier()
+    sus_ms = statistics.mean(sev[i].elapsed_time(sev[i + 1]) for i in range(sus_n // 2, sus_n))
 
     # roofline of the dominant kernel (fused unpack+FIR+FFT: one launch per step), rank-0 numbers
     peak, peak_src = _peak_hbm()

@@ -258,8 +258,10 @@ class Channelizer:
     def _pdw_call(self, fn, params, *lead):
         L = lib()
         n = C.c_uint64(0)
-        cap = max(256, 2 * getattr(self, "_last_pdw_count", 0))      # one call in the common case; a fresh array per call
-        arr = (Pdw * cap)()
+        # one call in the common case; a fresh array per call (the caller keeps the table), but neither a fresh array
+        # TYPE per call (capacities are powers of two, ctypes caches the types) nor a zero-filled one (numpy memory)
+        cap = max(256, 1 << (2 * getattr(self, "_last_pdw_count", 0)).bit_length())
+        arr = (Pdw * cap).from_buffer(np.empty(cap * C.sizeof(Pdw), dtype=np.uint8))
         rc = fn(self._h, C.byref(params), *lead, C.cast(arr, C.c_void_p), cap, C.byref(n))
         cnt = int(n.value)
         if rc == _lib.CHZ_ECAPACITY:   # the run cached its records in the handle; copy them out without recomputing

@@ -34,7 +34,19 @@ LaunchPlan plan_spans(const ::chz* h, long long nrows, int P, int groups_per_blo
   sr = (sr + P - 1) / P * P;
   static const long long span_cap = std::getenv("CHZ_SPAN_CAP") ? std::atoll(std::getenv("CHZ_SPAN_CAP")) : 4096;   // tuning aid
   const long long lo = 4LL * P, hi = (span_cap / P) * P;
-  if (sr < lo) sr = lo;
+  if (sr < lo) {
+    // Small call (a 100 ms file): at the shortest span there are between one and four spans per group, handed out
+    // round-robin, so a partial last round costs a whole one (342 spans on 296 groups: two rounds for 1.16 rounds of
+    // work).  Take the span length that minimises rounds x (rows + warm-up rows) instead.
+    long long best = -1, best_sr = lo;
+    for (long long c = lo; c <= hi && c <= 8 * lo; c += P) {
+      const long long nsp = (rows_per_phase + c - 1) / c * h->os, rounds = (nsp + total_groups - 1) / total_groups;
+      const long long cost = rounds * (c + P);
+      if (best < 0 || cost < best) { best = cost; best_sr = c; }
+      if (rounds == 1) break;                       // longer spans only add rows from here on
+    }
+    sr = best_sr;
+  }
   if (sr > hi) sr = hi;
   lp.span_rows = (int)sr;
   lp.spans_per_phase = (rows_per_phase + sr - 1) / sr;
@@ -522,6 +534,7 @@ int chz_create(uint32_t M, const float* taps, uint32_t ntaps, uint32_t oversampl
     CHZ_TRY(cudaMemcpy(h->d_twn, twn.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
   }
   if (const char* e = std::getenv("CHZ_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(e));   // tuning aid: 32 / 64 / 128
+  if (const char* e = std::getenv("CHZ_PDW_GRAPH")) h->pdw_use_graph = std::atoi(e) != 0;
   if (const char* e = std::getenv("CHZ_RING_UNPACK")) h->ring_unpack = std::atoi(e);          // tuning aids
   if (const char* e = std::getenv("CHZ_RING_VARIANT")) h->ring_variant = std::atoi(e);
   if (const char* e = std::getenv("CHZ_RING_DBG")) h->ring_dbg = std::atoi(e);
@@ -568,6 +581,7 @@ void chz_destroy(chz_t* h) {
   for (int i = 0; i < 4; i++) { if (h->ev_fir[i]) cudaEventDestroy(h->ev_fir[i]); if (h->ev_fft[i]) cudaEventDestroy(h->ev_fft[i]); }
   for (chzi::Scratch* sc : {&h->pdw_hist, &h->pdw_sel, &h->pdw_thr, &h->pdw_cnt, &h->pdw_ev, &h->pdw_pin, &h->pdw_pout, &h->pdw_code, &h->pdw_nf, &h->pdw_fast}) sc->release();
   if (h->pdw_stage_host) cudaFreeHost(h->pdw_stage_host);
+  if (h->pdw_graph) cudaGraphExecDestroy(h->pdw_graph);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
