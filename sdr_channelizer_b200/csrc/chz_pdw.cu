@@ -37,11 +37,138 @@ __device__ __forceinline__ int pass_shift(int pass) { return pass == 0 ? 20 : (p
 __device__ __forceinline__ uint32_t pass_mask(int pass) { return pass == 2 ? 0x1FFu : 0x7FFu; }
 __device__ __forceinline__ uint32_t prefix_mask(int pass) { return pass == 0 ? 0u : (pass == 1 ? 0xFFF00000u : 0xFFFFFE00u); }
 
+// ge = smallest float >= the leading threshold, le = largest float <= the trailing one; ge2 / le2 = the same two
+// decisions on the SQUARED magnitude: |y| >= ge <=> |y|^2 >= ge2 and |y| <= le <=> |y|^2 <= le2 for every float |y|^2,
+// because |y| = sqrt_rn(|y|^2) is monotone (squared_bounds walks to the exact boundaries).  The detector never takes
+// a square root.
+struct Thr { float ge, le, ge2, le2; };
+__host__ __device__ inline float sqrt_rn_(float x) {
+#ifdef __CUDA_ARCH__
+  return __fsqrt_rn(x);
+#else
+  return sqrtf(x);                                       // IEEE: correctly rounded, like sqrt.rn.f32
+#endif
+}
+__host__ __device__ inline float bits_step_(float x, int d) {   // next (d = +1) / previous (d = -1) float of a non-negative x
+  uint32_t b;
+  memcpy(&b, &x, 4);
+  b += (uint32_t)d;
+  memcpy(&x, &b, 4);
+  return x;
+}
+__host__ __device__ inline void squared_bounds(Thr* t) {
+  const float ge = t->ge, le = t->le, big = 3.402823466e38f;
+  // ge2 = the smallest x >= 0 with sqrt_rn(x) >= ge
+  if (ge != ge) t->ge2 = ge;                             // NaN: never true, like the comparison with ge itself
+  else if (!(ge > 0.f)) t->ge2 = 0.f;                    // every magnitude qualifies
+  else if (ge > big) t->ge2 = ge;                        // +inf
+  else {
+    float x = ge * ge;
+    if (x > big) x = big;
+    for (int i = 0; i < 64 && x > 0.f && sqrt_rn_(x) >= ge; i++) x = bits_step_(x, -1);
+    for (int i = 0; i < 64 && sqrt_rn_(x) < ge; i++) x = bits_step_(x, +1);      // steps from FLT_MAX to +inf if need be
+    t->ge2 = x;
+  }
+  // le2 = the largest x with sqrt_rn(x) <= le (none if le < 0)
+  if (le != le) t->le2 = le;
+  else if (le < 0.f) t->le2 = -1.f;
+  else if (le > big) t->le2 = le;
+  else {
+    float x = le * le;
+    if (x > big) x = big;
+    for (int i = 0; i < 64 && x <= big && sqrt_rn_(x) <= le; i++) x = bits_step_(x, +1);
+    for (int i = 0; i < 64 && x > 0.f && sqrt_rn_(x) > le; i++) x = bits_step_(x, -1);
+    t->le2 = x;
+  }
+}
+__device__ __forceinline__ void thresholds_of(const SelState& s, double scale, double scale_lo, Thr* thr, double* nf);
+
+// One 256-thread block and one channel: find the bucket holding each wanted rank, fix its bits, reduce the rank, clear
+// the channel's histogram rows for the next pass.  All threads of the block call it.
+// thr != NULL (last pass of the one-GPU extractor): the noise floor and the thresholds are derived right here,
+// which saves the k_thresholds launch.
+struct SelArgs { uint32_t rank_lo, rank_hi; double scale, scale_lo; Thr* thr; double* nf; };
+__device__ __forceinline__ void select_channel(uint32_t* __restrict__ hist, SelState* __restrict__ st, int pass, int ch,
+                                               const SelArgs& sa, uint32_t* scratch /* shared, 2 * 256 + 4 words */) {
+  uint32_t* const res_bin = scratch + 512;
+  uint32_t* const res_rank = scratch + 514;
+  const uint32_t rank_lo = sa.rank_lo, rank_hi = sa.rank_hi;
+  const double scale = sa.scale, scale_lo = sa.scale_lo;
+  Thr* const thr = sa.thr;
+  double* const nf = sa.nf;
+  SelState s;
+  if (pass == 0) { s.prefix[0] = s.prefix[1] = 0; s.rank[0] = rank_lo; s.rank[1] = rank_hi; }
+  else s = st[ch];
+  const bool split = pass > 0 && s.prefix[0] != s.prefix[1];
+  const int nb = pass == 2 ? 512 : kBins, per = nb / 256;
+  // 256 partial sums per slot, then warp `slot` finds the bucket that holds the wanted rank with a prefix sum
+  // across its lanes (one thread walking 256 partial sums took 10-15 us per pass)
+  uint32_t (*part2)[256] = reinterpret_cast<uint32_t (*)[256]>(scratch);
+  for (int slot = 0; slot < 2; slot++) {
+    const uint32_t* hrow = hist + ((size_t)ch * 2 + ((slot == 1 && split) ? 1 : 0)) * kBins;
+    uint32_t loc = 0;
+    for (int i = 0; i < per; i++) loc += hrow[threadIdx.x * per + i];
+    part2[slot][threadIdx.x] = loc;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < 2) {
+    const int slot = warp;
+    const uint32_t* hrow = hist + ((size_t)ch * 2 + ((slot == 1 && split) ? 1 : 0)) * kBins;
+    const uint32_t want = s.rank[slot];
+    uint32_t c[8], sum = 0;
+    #pragma unroll
+    for (int j = 0; j < 8; j++) { c[j] = part2[slot][lane * 8 + j]; sum += c[j]; }
+    uint32_t incl = sum;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const uint32_t excl = incl - sum;
+    const bool here = excl <= want && want < incl;
+    const unsigned any = __ballot_sync(0xffffffffu, here);
+    if (here || (any == 0 && lane == 31)) {          // no lane qualifies only if want >= total: clamp to the last bucket
+      uint32_t acc = excl;
+      int t = lane * 8;
+      #pragma unroll
+      for (int j = 0; j < 7; j++) {
+        if (t == lane * 8 + j) { if (acc + c[j] > want) { /* found */ } else { acc += c[j]; t++; } }
+      }
+      int b = t * per;
+      for (; b < t * per + per - 1; b++) { if (acc + hrow[b] > want) break; acc += hrow[b]; }
+      res_bin[slot] = (uint32_t)b;
+      res_rank[slot] = want - acc;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
+    for (int slot = 0; slot < 2; slot++) { s.prefix[slot] |= res_bin[slot] << shift; s.rank[slot] = res_rank[slot]; }
+    st[ch] = s;
+    if (thr) thresholds_of(s, scale, scale_lo, thr + ch, nf + ch);
+  }
+  __syncthreads();
+  // clear both histogram rows of this channel for the next pass
+  for (int i = threadIdx.x; i < 2 * kBins; i += 256) hist[(size_t)ch * 2 * kBins + i] = 0;
+  __syncthreads();                                       // callers loop over channels: the shared scratch is reused
+}
+// one block per channel (time-sharded extraction, where the host sums the shards' histograms between the passes)
+__global__ void __launch_bounds__(256) k_select(uint32_t* __restrict__ hist, SelState* __restrict__ st, int pass, SelArgs sa) {
+  __shared__ uint32_t scratch[2 * 256 + 4];
+  select_channel(hist, st, pass, blockIdx.x, sa, scratch);
+}
+
+
 // grid: (channel groups of 4, row chunks).  block 256 = 64 rows x 4 channels per step (32-byte row
 // segments, i.e. whole DRAM sectors).
 // hist: [M][2][kBins] uint32.  Slot 0 is privatised in shared memory; slot 1 (only used when the two
 // order statistics have diverged into different buckets) goes straight to global atomics.
-__global__ void __launch_bounds__(256) k_hist(const float2* __restrict__ y, long long nrows, int M, int pass,
+// Tried and removed: running the select inside this launch, by the block that finishes a channel slab last (a ticket
+// per slab): the four selects of a slab then run one after the other in ONE block at the tail of the launch (about
+// 5 us each: dependent global reads and four barriers) where k_select spreads them over M blocks -- 52 + 65 us for the
+// three passes against 34 + 46 us with the separate launches.
+__global__ void __launch_bounds__(256, 6) k_hist(const float2* __restrict__ y, long long nrows, int M, int pass,
                                               const SelState* __restrict__ st, uint32_t* __restrict__ hist) {
   __shared__ __align__(16) uint32_t sh[4 * kBins];
   // on 100 ms files a block bins ~1 400 rows x 4 channels into 8 192 counters: clearing and flushing them costs as
@@ -101,74 +228,6 @@ __global__ void __launch_bounds__(256) k_hist(const float2* __restrict__ y, long
   }
 }
 
-// one block per channel: find the bucket holding each wanted rank, fix its bits, reduce the rank
-struct Thr { float ge, le; };   // ge = smallest float >= the leading threshold, le = largest float <= the trailing one
-__device__ __forceinline__ void thresholds_of(const SelState& s, double scale, double scale_lo, Thr* thr, double* nf);
-
-// thr != NULL (last pass of the one-GPU extractor): the noise floor and the thresholds are derived right here,
-// which saves the k_thresholds launch
-__global__ void __launch_bounds__(256) k_select(uint32_t* __restrict__ hist, SelState* __restrict__ st, int pass,
-                                                uint32_t rank_lo, uint32_t rank_hi, double scale, double scale_lo,
-                                                Thr* __restrict__ thr, double* __restrict__ nf) {
-  __shared__ uint32_t res_bin[2], res_rank[2];
-  const int ch = blockIdx.x;
-  SelState s;
-  if (pass == 0) { s.prefix[0] = s.prefix[1] = 0; s.rank[0] = rank_lo; s.rank[1] = rank_hi; }
-  else s = st[ch];
-  const bool split = pass > 0 && s.prefix[0] != s.prefix[1];
-  const int nb = pass == 2 ? 512 : kBins, per = nb / 256;
-  // 256 partial sums per slot, then warp `slot` finds the bucket that holds the wanted rank with a prefix sum
-  // across its lanes (one thread walking 256 partial sums took 10-15 us per pass)
-  __shared__ uint32_t part2[2][256];
-  for (int slot = 0; slot < 2; slot++) {
-    const uint32_t* hrow = hist + ((size_t)ch * 2 + ((slot == 1 && split) ? 1 : 0)) * kBins;
-    uint32_t loc = 0;
-    for (int i = 0; i < per; i++) loc += hrow[threadIdx.x * per + i];
-    part2[slot][threadIdx.x] = loc;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < 2) {
-    const int slot = warp;
-    const uint32_t* hrow = hist + ((size_t)ch * 2 + ((slot == 1 && split) ? 1 : 0)) * kBins;
-    const uint32_t want = s.rank[slot];
-    uint32_t c[8], sum = 0;
-    #pragma unroll
-    for (int j = 0; j < 8; j++) { c[j] = part2[slot][lane * 8 + j]; sum += c[j]; }
-    uint32_t incl = sum;
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
-    }
-    const uint32_t excl = incl - sum;
-    const bool here = excl <= want && want < incl;
-    const unsigned any = __ballot_sync(0xffffffffu, here);
-    if (here || (any == 0 && lane == 31)) {          // no lane qualifies only if want >= total: clamp to the last bucket
-      uint32_t acc = excl;
-      int t = lane * 8;
-      #pragma unroll
-      for (int j = 0; j < 7; j++) {
-        if (t == lane * 8 + j) { if (acc + c[j] > want) { /* found */ } else { acc += c[j]; t++; } }
-      }
-      int b = t * per;
-      for (; b < t * per + per - 1; b++) { if (acc + hrow[b] > want) break; acc += hrow[b]; }
-      res_bin[slot] = (uint32_t)b;
-      res_rank[slot] = want - acc;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
-    for (int slot = 0; slot < 2; slot++) { s.prefix[slot] |= res_bin[slot] << shift; s.rank[slot] = res_rank[slot]; }
-    st[ch] = s;
-    if (thr) thresholds_of(s, scale, scale_lo, thr + ch, nf + ch);
-  }
-  __syncthreads();
-  // clear both histogram rows of this channel for the next pass
-  for (int i = threadIdx.x; i < 2 * kBins; i += 256) hist[(size_t)ch * 2 * kBins + i] = 0;
-}
-
 // ---- edge detection -----------------------------------------------------------------------------------
 // Leading edge: mag >= T_lead <=> mag >= ge (ge = smallest float >= T_lead).  Trailing edge: mag <= T_trail <=>
 // mag <= le (le = largest float <= T_trail).  The channelized script uses one threshold for both
@@ -196,6 +255,7 @@ __device__ __forceinline__ void thresholds_of(const SelState& s, double scale, d
   Thr t;
   t.ge = float_ge(v * scale);
   t.le = float_le(v * scale_lo);
+  squared_bounds(&t);
   *thr = t;
 }
 __global__ void k_thresholds(const SelState* __restrict__ st, int M, double scale, double scale_lo, Thr* __restrict__ thr,
@@ -258,36 +318,55 @@ __global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, lo
     bool flips = false;
     long long j = r0 - 1;
     for (; j >= 0; j--) {
-      const float m = mag_of(y[j * M + ch]);
-      if (exact && m == t.ge) { flips = !flips; if (PULSES) count[1] = 1; continue; }
-      if (m >= t.ge) { active = true; break; }
-      if (m <= t.le) { active = false; break; }
+      const float m2 = mag2_of(y[j * M + ch]);
+      const bool a = m2 >= t.ge2, b = m2 <= t.le2;
+      if (exact && a && b) { flips = !flips; if (PULSES) count[1] = 1; continue; }
+      if (a) { active = true; break; }
+      if (b) { active = false; break; }
     }
     active = active != flips;
   }
   constexpr int UN = PULSES ? 16 : 8;                      // rows fetched ahead of the (sequential) state machine
   uint32_t last_below = 0xFFFFFFFFu, first_above = 0xFFFFFFFFu;   // PULSES: chunk summary (rows of this launch)
+  // Per batch of UN rows every lane first reduces its rows to two bit masks (bit u: row u is >= ge / <= le; no square
+  // root, see Thr) and updates the chunk summary from them with bit scans.  A lane's state can only change in a batch
+  // in which an inactive channel sees a row >= ge or an active one a row <= le; if no lane of the warp is in that
+  // position -- the rule between pulses -- the batch is done.  Otherwise the warp walks the batch row by row with a
+  // ballot per row as before.  (ncu before: 60 warp instructions per element, 31 us per 45 MB.)
   for (int i0 = 0; i0 < chunk_rows; i0 += UN) {            // lock-step over the chunk
+    const long long rb = r0 + i0;
     float2 v[UN];
     #pragma unroll
-    for (int u = 0; u < UN; u++) {
-      const long long r = r0 + i0 + u;
-      v[u] = (live && r < r1) ? __ldg(y + r * M + ch) : make_float2(0.f, 0.f);
-    }
+    for (int u = 0; u < UN; u++) v[u] = (live && rb + u < r1) ? __ldg(y + (rb + u) * M + ch) : make_float2(0.f, 0.f);
+    uint32_t A = 0, B = 0;
     #pragma unroll
     for (int u = 0; u < UN; u++) {
-      const long long r = r0 + i0 + u;
-      bool ev = false;
-      if (live && r < r1) {
-        const float m = mag_of(v[u]);
-        if (PULSES) {
-          if (exact && m == t.ge) count[1] = 1;
-          if (m <= t.le) { last_below = (uint32_t)r; first_above = 0xFFFFFFFFu; }
-          else if (m >= t.ge && first_above == 0xFFFFFFFFu) first_above = (uint32_t)r;
-        }
-        if (!active) { if (m >= t.ge) { active = true; ev = !PULSES; lead = r; } }   // leading edge (:88)
-        else if (m <= t.le) { active = false; ev = true; }                            // trailing edge (:94)
+      const float m2 = mag2_of(v[u]);
+      A |= (m2 >= t.ge2 ? 1u : 0u) << u;
+      B |= (m2 <= t.le2 ? 1u : 0u) << u;
+    }
+    const long long left = live ? r1 - rb : 0;            // rows of this batch that exist
+    const uint32_t vmask = left >= UN ? (1u << UN) - 1u : (left > 0 ? (1u << (int)left) - 1u : 0u);
+    A &= vmask; B &= vmask;
+    if (PULSES) {
+      if (exact && (A & B)) count[1] = 1;
+      if (B) {
+        const int hb = 31 - __clz(B);
+        last_below = (uint32_t)(rb + hb);
+        const uint32_t after = A & ~((2u << hb) - 1u);
+        first_above = after ? (uint32_t)(rb + __ffs(after) - 1) : 0xFFFFFFFFu;
+      } else if (A && first_above == 0xFFFFFFFFu) {
+        first_above = (uint32_t)(rb + __ffs(A) - 1);
       }
+    }
+    if (!__any_sync(0xffffffffu, active ? B != 0u : A != 0u)) continue;
+    #pragma unroll
+    for (int u = 0; u < UN; u++) {
+      const long long r = rb + u;
+      bool ev = false;
+      const bool a = (A >> u) & 1u, b = (B >> u) & 1u;
+      if (!active) { if (a) { active = true; ev = !PULSES; lead = r; } }   // leading edge (:88)
+      else if (b) { active = false; ev = true; }                            // trailing edge (:94)
       const unsigned ball = __ballot_sync(0xffffffffu, ev);
       if (ball) {
         unsigned long long base = 0;
@@ -324,10 +403,11 @@ __global__ void __launch_bounds__(128) k_exit_state(const float2* __restrict__ y
   bool flips = false;
   int c = 2;
   for (long long j = nrows - 1; j >= 0; j--) {
-    const float m = mag_of(y[j * M + ch]);
-    if (exact && m == t.ge) { flips = !flips; continue; }
-    if (m >= t.ge) { c = 1; break; }
-    if (m <= t.le) { c = 0; break; }
+    const float m2 = mag2_of(y[j * M + ch]);
+    const bool a = m2 >= t.ge2, b = m2 <= t.le2;
+    if (exact && a && b) { flips = !flips; continue; }
+    if (a) { c = 1; break; }
+    if (b) { c = 0; break; }
   }
   code[ch] = (uint8_t)(c == 2 ? (flips ? 3 : 2) : (flips ? 1 - c : c));
 }
@@ -532,6 +612,26 @@ static int pdw_buffers(::chz* h) {
   return CHZ_OK;
 }
 
+static void threshold_scales(const chz_pdw_params_t* prm, double* scale, double* scale_lo) {
+  *scale = std::pow(10.0, prm->snr_threshold_db / 10.0);
+  // create_pdws.m:47: TRAILING_EDGE_THRESHOLD = NOISE_FLOOR*10^(3/10); never above the leading threshold
+  const bool hyst = prm->use_trailing_threshold != 0 && prm->trailing_snr_threshold_db < prm->snr_threshold_db;
+  *scale_lo = hyst ? std::pow(10.0, prm->trailing_snr_threshold_db / 10.0) : *scale;
+}
+
+// arguments of one select: the two middle ranks of total_rows values; prm != NULL on the last pass: noise floor ->
+// nf_dev and thresholds -> h->pdw_thr in the same step
+static int make_sel_args(::chz* h, uint64_t total_rows, const chz_pdw_params_t* prm, double* nf_dev, SelArgs* sa) {
+  if (total_rows == 0 || total_rows > 0xFFFFFFFFull) return CHZ_EINVAL;
+  sa->rank_lo = (uint32_t)((total_rows - 1) / 2);
+  sa->rank_hi = (uint32_t)(total_rows / 2);
+  sa->scale = sa->scale_lo = 0.0;
+  if (prm) threshold_scales(prm, &sa->scale, &sa->scale_lo);
+  sa->thr = prm ? (Thr*)h->pdw_thr.p : nullptr;
+  sa->nf = nf_dev;
+  return CHZ_OK;
+}
+
 // local histogram of one radix pass (:73); pass 0 clears the table first (k_select clears it after every pass)
 static int pdw_hist_pass(::chz* h, const float2* y, uint64_t nrows, int pass) {
   const int M = (int)h->M;
@@ -566,21 +666,13 @@ static int pdw_hist_pass(::chz* h, const float2* y, uint64_t nrows, int pass) {
 
 // fix the next bits of both middle order statistics from the (summed) histogram; total_rows = rows of the
 // WHOLE recording
-static void threshold_scales(const chz_pdw_params_t* prm, double* scale, double* scale_lo) {
-  *scale = std::pow(10.0, prm->snr_threshold_db / 10.0);
-  // create_pdws.m:47: TRAILING_EDGE_THRESHOLD = NOISE_FLOOR*10^(3/10); never above the leading threshold
-  const bool hyst = prm->use_trailing_threshold != 0 && prm->trailing_snr_threshold_db < prm->snr_threshold_db;
-  *scale_lo = hyst ? std::pow(10.0, prm->trailing_snr_threshold_db / 10.0) : *scale;
-}
 
 // prm != NULL on the last pass: noise floor -> nf_dev and thresholds -> h->pdw_thr in the same launch
 static int pdw_select_pass(::chz* h, int pass, uint64_t total_rows, const chz_pdw_params_t* prm = nullptr, double* nf_dev = nullptr) {
-  if (total_rows == 0 || total_rows > 0xFFFFFFFFull) return CHZ_EINVAL;
-  const uint32_t rank_lo = (uint32_t)((total_rows - 1) / 2), rank_hi = (uint32_t)(total_rows / 2);
-  double scale = 0.0, scale_lo = 0.0;
-  if (prm) threshold_scales(prm, &scale, &scale_lo);
-  k_select<<<h->M, 256, 0, h->stream>>>((uint32_t*)h->pdw_hist.p, (SelState*)h->pdw_sel.p, pass, rank_lo, rank_hi, scale, scale_lo,
-                                         prm ? (Thr*)h->pdw_thr.p : nullptr, nf_dev);
+  SelArgs sa;
+  const int rc = make_sel_args(h, total_rows, prm, nf_dev, &sa);
+  if (rc) return rc;
+  k_select<<<h->M, 256, 0, h->stream>>>((uint32_t*)h->pdw_hist.p, (SelState*)h->pdw_sel.p, pass, sa);
   h->launches++;
   CHZ_CUDA(cudaGetLastError());
   return CHZ_OK;
@@ -1012,6 +1104,7 @@ int chz_pdw_shard_set_noise_floor(chz_t* h, const chz_pdw_params_t* params, cons
     if ((double)ge < tl) ge = std::nextafterf(ge, INFINITY);
     if ((double)le > tt) le = std::nextafterf(le, -INFINITY);
     thr[k].ge = ge; thr[k].le = le;
+    squared_bounds(&thr[k]);
   }
   h->noise_floor.assign(noise_floor, noise_floor + M);
   h->pdws.clear();
