@@ -979,24 +979,34 @@ static int pdw_extract_fast(::chz* h, const chz_pdw_params_t* prm, const float2*
     memcpy(h->noise_floor.data(), (const unsigned char*)h->pdw_stage_host + 16, sizeof(double) * M);
     if (hc[1]) return 1;                               // equality on a representable threshold: event path
     if (n > cap) { h->pdw_pulse_cap = n + n / 4; continue; }
-    std::vector<PulseRec> recs(n);
+    // the records usually all sit in the pinned landing zone already; only a longer list needs a second copy
     const unsigned long long got = std::min(n, first);
-    if (got) memcpy(recs.data(), (const unsigned char*)h->pdw_stage_host + head, got * sizeof(PulseRec));
+    const PulseRec* recs = (const PulseRec*)((const unsigned char*)h->pdw_stage_host + head);
+    std::vector<PulseRec> more;
     if (n > got) {
-      CHZ_CUDA(cudaMemcpyAsync(recs.data() + got, d_rec + got, (n - got) * sizeof(PulseRec), cudaMemcpyDeviceToHost, st));
+      more.resize(n);
+      memcpy(more.data(), recs, got * sizeof(PulseRec));
+      CHZ_CUDA(cudaMemcpyAsync(more.data() + got, d_rec + got, (n - got) * sizeof(PulseRec), cudaMemcpyDeviceToHost, st));
       CHZ_CUDA(cudaStreamSynchronize(st));
+      recs = more.data();
     }
-    // the script's order (shifted channel, then time of arrival): sort 16-byte keys, not 100-byte records, and build
-    // each record once, in place (sorting the records themselves cost more host time than the detector costs GPU time)
-    std::vector<std::pair<unsigned long long, unsigned long long>> order(n);
-    for (unsigned long long i = 0; i < n; i++) {
-      const unsigned long long c = (recs[i].in.k + (uint32_t)(M / 2)) % (uint32_t)M;
-      order[i] = std::make_pair((c << 48) | recs[i].in.toa, i);       // toa_row < 2^48
+    // The script's order (shifted channel, then time of arrival).  The device list is in no particular order across
+    // channels and nearly in time order within one: a counting sort by channel, then a small sort per channel, on
+    // indices -- each 100-byte record is built once, in its final place (sorting the records themselves cost more host
+    // time than the detector costs GPU time).
+    std::vector<uint32_t> start((size_t)M + 1, 0u), idx(n);
+    for (unsigned long long i = 0; i < n; i++) start[(recs[i].in.k + (uint32_t)(M / 2)) % (uint32_t)M + 1]++;
+    for (int c = 0; c < M; c++) start[c + 1] += start[c];
+    {
+      std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+      for (unsigned long long i = 0; i < n; i++) idx[fill[(recs[i].in.k + (uint32_t)(M / 2)) % (uint32_t)M]++] = (uint32_t)i;
     }
-    std::sort(order.begin(), order.end());
+    for (int c = 0; c < M; c++)
+      if (start[c + 1] - start[c] > 1)
+        std::sort(idx.begin() + start[c], idx.begin() + start[c + 1], [&](uint32_t x, uint32_t y2) { return recs[x].in.toa < recs[y2].in.toa; });
     h->pdws.resize(n);
     for (unsigned long long i = 0; i < n; i++) {
-      const PulseRec& q = recs[order[i].second];
+      const PulseRec& q = recs[idx[i]];
       h->pdws[i] = make_record(h, prm, q.in.k, q.in.toa, q.in.end, q.out);
     }
     if (gtrace)
