@@ -212,7 +212,13 @@ __global__ void __launch_bounds__(256, 6) k_hist(const float2* __restrict__ y, l
       #pragma unroll
       for (int u = 0; u < UN; u++) bin_one(v[u]);
     }
-    for (; r < r_end; r += 64, p += rstep) bin_one(__ldg(p));
+    if (r < r_end) {                                       // last, partial batch: the same loads in flight, with row checks
+      float2 v[UN];
+      #pragma unroll
+      for (int u = 0; u < UN; u++) v[u] = r + 64LL * u < r_end ? __ldg(p + u * rstep) : make_float2(0.f, 0.f);
+      #pragma unroll
+      for (int u = 0; u < UN; u++) if (r + 64LL * u < r_end) bin_one(v[u]);
+    }
   }
   __syncthreads();
   for (int i4 = threadIdx.x; i4 < kBins; i4 += 256) {
@@ -333,11 +339,20 @@ __global__ void __launch_bounds__(256) k_detect(const float2* __restrict__ y, lo
   // in which an inactive channel sees a row >= ge or an active one a row <= le; if no lane of the warp is in that
   // position -- the rule between pulses -- the batch is done.  Otherwise the warp walks the batch row by row with a
   // ballot per row as before.  (ncu before: 60 warp instructions per element, 31 us per 45 MB.)
+  // The next batch's rows are requested before this batch is looked at: with a few dozen warps per SM each walking its
+  // chunk batch by batch, the memory latency of every batch was in the open.
+  float2 vn[UN];
+  #pragma unroll
+  for (int u = 0; u < UN; u++) vn[u] = (live && r0 + u < r1) ? __ldg(y + (r0 + u) * M + ch) : make_float2(0.f, 0.f);
   for (int i0 = 0; i0 < chunk_rows; i0 += UN) {            // lock-step over the chunk
     const long long rb = r0 + i0;
     float2 v[UN];
     #pragma unroll
-    for (int u = 0; u < UN; u++) v[u] = (live && rb + u < r1) ? __ldg(y + (rb + u) * M + ch) : make_float2(0.f, 0.f);
+    for (int u = 0; u < UN; u++) v[u] = vn[u];
+    if (i0 + UN < chunk_rows) {
+      #pragma unroll
+      for (int u = 0; u < UN; u++) vn[u] = (live && rb + UN + u < r1) ? __ldg(y + (rb + UN + u) * M + ch) : make_float2(0.f, 0.f);
+    }
     uint32_t A = 0, B = 0;
     #pragma unroll
     for (int u = 0; u < UN; u++) {
