@@ -276,7 +276,7 @@ class TorchDistComm:
         width = max(max(sizes), 1)
         mine = torch.zeros(width, dtype=torch.uint8, device=dev)
         if arr.nbytes:
-            mine[:arr.nbytes] = torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(dev)
+            mine[:arr.nbytes] = torch.from_numpy(np.array(arr.view(np.uint8).reshape(-1))).to(dev)   # a copy: the source may be read-only
         allb = torch.empty(self.world * width, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allb, mine, group=self.group)
         host = allb.cpu().numpy()
