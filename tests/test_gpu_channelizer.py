@@ -452,3 +452,17 @@ def test_channelizer_example_script(orc, tmp_path):
     z = frames[-1][2]
     col = int(np.argmax(z.mean(axis=0)))
     assert abs(frames[-1][0][col] - (fc * 1e-6 + 1.0)) < 1e-9        # strongest tone: centre 1 -> -1 MHz offset -> f = fc + 1
+
+
+def test_ring_kernel_random_shapes_are_repeatable_and_match_the_split_path():
+    """tools/exp/ring_stress.py: random lengths, chunkings, bit widths, oversampling, taps per band and input
+    alignments through the M = 1024 kernel (FIR warps and FFT warps handing tiles over through named barriers, TMA
+    ring with mbarriers).  Three runs of a case must be bit-identical -- compute-sanitizer's racecheck is closed on
+    this pool, and a race would show as nondeterminism -- and agree with the split path to rel-RMS 1e-5."""
+    import subprocess
+    import sys
+    _torch()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "exp", "ring_stress.py"), "24"], capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, SEED="11"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
