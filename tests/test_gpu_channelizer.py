@@ -1,6 +1,7 @@
 """Parity tests proper: the CUDA path through the C ABI against the CPU oracle, on a real B200.
 Tolerances are north_star's: unpack bit-exact; channel outputs rel. RMS <= 1e-5 vs the double oracle."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
