@@ -230,6 +230,11 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, fl
     dft<R>(v);
     const int j0 = (j - k) * R + k;     // (j / NS) * NS * R + k
     if (LAST) {
+      // Tried: swapping every other result with the neighbouring lane (adjacent lanes hold adjacent channels) so that
+      // each lane stores 16 bytes -- 512-byte runs per warp instruction.  A do-nothing kernel with this traffic mix
+      // runs 7 % faster with 8-byte loads / 16-byte stores than with 4 / 8 (tools/ubench/mixbw.cu), but here the two
+      // shuffles per pair land on the LSU pipe, the busiest unit of the fused kernels: M = 64 442.8 -> 360.6 GS/s,
+      // M = 32 459.7 -> 324.7, M = 256 352.5 -> 327.5 (profiles/r02o_paired_stores_ab.jsonl).  Removed.
       if (row >= vlo && row < vhi) {
         float2* g = gout + (long long)row * grow_stride;
         #pragma unroll
