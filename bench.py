@@ -457,8 +457,9 @@ def main():
 
     # What a do-nothing kernel with the SAME traffic reaches on this board: K1 alone (int16 pair -> float2: 4 B read,
     # 8 B written per sample) over the same buffers.  The copy peak in MEASURED_PEAKS.json is a 1:1 read:write mix;
-    # this path writes twice what it reads, and no kernel we tried moves that mix faster than K1 does
-    # (tools/ubench/mixbw.cu: 128-bit variants 4.6-5.1 TB/s, K1 5.6 TB/s, copy 6.5 TB/s).
+    # this path writes twice what it reads.  K1 (two samples per thread, 8-byte loads, 16-byte stores) reaches ~95 %
+    # of the copy peak with that mix (tools/ubench/mixbw.cu has the variants), so the gap between the fused kernel
+    # and K1 is what the FIR and the FFT cost on top of the traffic.
     # Measured right after the timed region, before the 200-launch sustained run heats the board.
     same_traffic = None
     if BIT_WIDTH > 8 and OVERSAMPLE == 1:

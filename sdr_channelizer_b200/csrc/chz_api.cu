@@ -772,12 +772,27 @@ int chz_unpack_dev(const void* iq_dev, uint64_t nsamp, uint32_t bit_width, chz_c
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return CHZ_ENODEVICE; }
   if (!nsamp) return CHZ_OK;
   const float scale = std::ldexp(1.0f, -(int)(bit_width - 1));
-  long long blocks = ((long long)nsamp + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  if (bit_width > 8) k_unpack<true><<<(unsigned)blocks, 256, 0, st>>>(iq_dev, (long long)nsamp, scale, (float2*)out_dev);
-  else k_unpack<false><<<(unsigned)blocks, 256, 0, st>>>(iq_dev, (long long)nsamp, scale, (float2*)out_dev);
-  CHZ_CUDA(cudaGetLastError());
+  const bool in16 = bit_width > 8;
+  const bool aligned = (((uintptr_t)iq_dev) & (in16 ? 7u : 3u)) == 0 && (((uintptr_t)out_dev) & 15u) == 0;
+  const long long n2 = aligned ? (long long)(nsamp / 2) : 0;     // sample pairs through the two-per-thread kernel
+  if (n2) {
+    long long blocks = (n2 + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (in16) k_unpack<true><<<(unsigned)blocks, 256, 0, st>>>(iq_dev, n2, scale, (float4*)out_dev);
+    else k_unpack<false><<<(unsigned)blocks, 256, 0, st>>>(iq_dev, n2, scale, (float4*)out_dev);
+    CHZ_CUDA(cudaGetLastError());
+  }
+  const long long rest = (long long)nsamp - 2 * n2;              // everything if misaligned, else 0 or 1 sample
+  if (rest) {
+    long long blocks = (rest + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    const char* src = (const char*)iq_dev + (size_t)(2 * n2) * (in16 ? 4 : 2);
+    float2* dst = (float2*)out_dev + 2 * n2;
+    if (in16) k_unpack1<true><<<(unsigned)blocks, 256, 0, st>>>(src, rest, scale, dst);
+    else k_unpack1<false><<<(unsigned)blocks, 256, 0, st>>>(src, rest, scale, dst);
+    CHZ_CUDA(cudaGetLastError());
+  }
   return CHZ_OK;
 }
 

@@ -57,6 +57,26 @@ def test_unpack_bit_exact_all_values(orc, bw):
     assert np.array_equal(got[:, 0].astype(np.float64), ref.real) and np.array_equal(got[:, 1].astype(np.float64), ref.imag)
 
 
+@pytest.mark.parametrize("bw,n,off_in,off_out", [(12, 1001, 0, 0), (12, 1000, 1, 0), (12, 999, 0, 1), (8, 777, 1, 1),
+                                                 (8, 4096, 0, 0), (16, 1, 0, 0), (16, 2, 3, 0)])
+def test_unpack_odd_counts_and_misaligned_buffers(orc, bw, n, off_in, off_out):
+    """K1 takes two samples per thread (8-byte loads, 16-byte stores) when the buffers allow it: an odd count leaves
+    one sample to the scalar kernel, a misaligned input or output sends the whole call there."""
+    torch = _torch()
+    rng = np.random.default_rng(n + bw)
+    lim = 2 ** (bw - 1)
+    iq = rng.integers(-lim, lim, size=(n + off_in, 2)).astype(np.int8 if bw <= 8 else np.int16)
+    d_in = torch.from_numpy(iq).cuda()
+    d_out = torch.full((n + off_out + 1, 2), -7.0, dtype=torch.float32, device="cuda")
+    pkg.unpack_ptr(d_in[off_in:].data_ptr(), n, bw, d_out[off_out:].data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    ref = orc.unpack(iq[off_in:], bw)
+    g = got[off_out:off_out + n]
+    assert np.array_equal(g[:, 0].astype(np.float64), ref.real) and np.array_equal(g[:, 1].astype(np.float64), ref.imag)
+    assert np.all(got[:off_out] == -7.0) and np.all(got[off_out + n:] == -7.0)       # nothing written outside
+
+
 # ---- K3 against cuFFT ----------------------------------------------------------------------------------
 @pytest.mark.parametrize("M", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 56, 560,   # 56 = 8*7, 560 = 16*5*7: radix-7/5 passes
                                2, 6, 7, 12, 40, 48, 100, 112, 120, 200, 243, 768, 1000, 3000, 3584,   # run-time mixed-radix plans
