@@ -101,16 +101,25 @@ __device__ __forceinline__ int tpad(int pos) { return pos + ((pos >> 7) << 1); }
 // Register split between the roles (setmaxnreg; the sum over 8 + 8 warps must stay within 65 536): the FIR code needs
 // 134 registers at P = 16.  A/B over 128/128, 136/120, 144/112, 152/104, 160/96: all within +-3 % (instruction
 // scheduling differences); 136/120 is best at P = 16 and 8, 152/104 at P = 12.
-template <int P> struct RoleRegs {
-  static constexpr int FIR = P == 12 ? 152 : 136, FFT = P == 12 ? 104 : 120;
-  static_assert(8 * 32 * (FIR + FFT) <= 65536, "register file");
+// FW = 16 FFT warps (768 threads: four row groups of two rows, one butterfly in flight per thread, 128/56 registers)
+// was built to give the FFT role more warps to hide its latencies with: 267 / 142 GS/s against 310 / 162 with FW = 8
+// (EXPERIMENTS build, CHZ_RING_VARIANT=3) -- at 56 registers the role spills and loses its two-butterfly batches.
+template <int P, int FW> struct RoleRegs {       // FW = FFT warps (8 or 16) next to the 8 FIR warps
+  static constexpr int FIR = FW == 16 ? 128 : (P == 12 ? 152 : 136);
+  static constexpr int FFT = FW == 16 ? 56 : (P == 12 ? 104 : 120);
+  // setmaxnreg.inc only gets what setmaxnreg.dec of the SAME block released: the budget is what the block was launched
+  // with (registers per thread rounded down to 8), not the whole register file -- asking for more waits for ever
+  static constexpr int LAUNCH = 65536 / (256 + 32 * FW) / 8 * 8;
+  static_assert(8 * 32 * FIR + FW * 32 * FFT <= (256 + 32 * FW) * LAUNCH, "register budget of the block");
 };
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-template <int P, bool IN16, int UNPACK>
-__global__ void __launch_bounds__(kNT, 1) k_chan_ring_ws(ChanParams prm, RingParams rp) {
+template <int P, bool IN16, int UNPACK, int FW = 8>
+__global__ void __launch_bounds__(256 + 32 * FW, 1) k_chan_ring_ws(ChanParams prm, RingParams rp) {
+  constexpr int NTH = 256 + 32 * FW;                 // threads of the block: every hand-off barrier counts them all
+  constexpr int NG = FW / 4, RG = kR / NG;           // FFT row groups of 128 threads, rows per group
   typedef Smem<IN16> SM;
   typedef typename RawT<IN16>::type raw_t;
   constexpr int M = kM, ROWB = SM::ROWB, SLOTB = SM::SLOTB, TS = kTileStride;
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring_ws(ChanParams prm, RingPar
 
   if (t < 256) {
     // =========================== FIR warps ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RoleRegs<P>::FIR));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RoleRegs<P, FW>::FIR));
     const int f = t;
     float hA1[P], hA2[P], hB1[P], hB2[P];           // taps of the column pairs u = f and u = f + 256
     {
@@ -196,7 +205,7 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring_ws(ChanParams prm, RingPar
       for (int ph = 0; ph < os; ph++, n++) {
         const int buf = (int)(n & 1);
         float2* tile = tiles + buf * (kR * TS);
-        if (n >= 2) bar_sync(BAR_EMPTY + buf, kNT);  // the FFT warps have drained this buffer (tile n - 2)
+        if (n >= 2) bar_sync(BAR_EMPTY + buf, NTH);  // the FFT warps have drained this buffer (tile n - 2)
         const int shift = ph ? D : 0;
         // one column pair: 8 rows x branches (2u+2, 2u+1)
         auto fir_pair = [&](int u, const float (&h1)[P], const float (&h2)[P]) {
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring_ws(ChanParams prm, RingPar
           fir_pair(f + 256, hB1, hB2);
           fix_branch0();
         }
-        bar_arrive(BAR_FULL + buf, kNT);             // tile n is complete
+        bar_arrive(BAR_FULL + buf, NTH);             // tile n is complete
       }
       // the oldest ring slot is dead once every FIR warp is through this step: request the next step's frames
       bar_sync(BAR_FIR, 256);
@@ -281,9 +290,10 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring_ws(ChanParams prm, RingPar
     }
   } else {
     // =========================== FFT warps ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RoleRegs<P>::FFT));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RoleRegs<P, FW>::FFT));
     const int g = t - 256;
-    const int rr = g >> 7, tg = g & 127;             // rows rr, rr+2, rr+4, rr+6 belong to the 4 warps g >> 7
+    const int rr = g >> 7, tg = g & 127;             // rows rr, rr + NG, rr + 2 NG, ... belong to the 4 warps g >> 7
+    constexpr int BT = FW == 8 ? 2 : 1;              // radix-8 butterflies in flight per thread (registers)
     float2 tw0[7];
     #pragma unroll
     for (int q = 1; q < 8; q++) tw0[q - 1] = __ldg(rp.twn + ((tg * q) & (M - 1)));
@@ -292,21 +302,29 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring_ws(ChanParams prm, RingPar
       float2* tile = tiles + buf * (kR * TS);
       const long long a0 = rp.a_lo + (k0 + n / os) * kR;
       const int ph = (int)(n % os);
-      bar_sync(BAR_FULL + buf, kNT);                 // the FIR warps have finished tile n
-      if (rp.dbg & 1) { bar_arrive(BAR_EMPTY + buf, kNT); continue; }
+      bar_sync(BAR_FULL + buf, NTH);                 // the FIR warps have finished tile n
+      if (rp.dbg & 1) { bar_arrive(BAR_EMPTY + buf, NTH); continue; }
       #pragma unroll
-      for (int hh = 0; hh < 2; hh++) {               // pass 0: four butterflies per thread, two at a time
-        float2* row0 = tile + (rr + 4 * hh) * TS + tg;
-        float2* row1 = row0 + 2 * TS;
-        float2 v[8], w[8];
+      for (int i0 = 0; i0 < RG; i0 += BT) {          // pass 0: one radix-8 butterfly per row of the group
+        float2 v[BT][8];
         #pragma unroll
-        for (int q = 0; q < 8; q++) { v[q] = row0[q * 130]; w[q] = row1[q * 130]; }
-        dft8(v);
-        dft8(w);
+        for (int bi = 0; bi < BT; bi++) {
+          const float2* row = tile + (rr + NG * (i0 + bi)) * TS + tg;
+          #pragma unroll
+          for (int q = 0; q < 8; q++) v[bi][q] = row[q * 130];
+        }
         #pragma unroll
-        for (int q = 1; q < 8; q++) { v[q] = cmul(v[q], tw0[q - 1]); w[q] = cmul(w[q], tw0[q - 1]); }
+        for (int bi = 0; bi < BT; bi++) {
+          dft8(v[bi]);
+          #pragma unroll
+          for (int q = 1; q < 8; q++) v[bi][q] = cmul(v[bi][q], tw0[q - 1]);
+        }
         #pragma unroll
-        for (int q = 0; q < 8; q++) { row0[q * 130] = v[q]; row1[q * 130] = w[q]; }
+        for (int bi = 0; bi < BT; bi++) {
+          float2* row = tile + (rr + NG * (i0 + bi)) * TS + tg;
+          #pragma unroll
+          for (int q = 0; q < 8; q++) row[q * 130] = v[bi][q];
+        }
       }
       bar_sync(BAR_FFT + rr, 128);
       {
@@ -315,24 +333,32 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring_ws(ChanParams prm, RingPar
         #pragma unroll
         for (int q = 1; q < 8; q++) tw[q - 1] = tw1s[(q - 1) * 16 + j1];
         #pragma unroll
-        for (int hh = 0; hh < 2; hh++) {             // pass 1
-          float2* row0 = tile + (rr + 4 * hh) * TS + kb * 130 + j1;
-          float2* row1 = row0 + 2 * TS;
-          float2 v[8], w[8];
+        for (int i0 = 0; i0 < RG; i0 += BT) {        // pass 1
+          float2 v[BT][8];
           #pragma unroll
-          for (int q = 0; q < 8; q++) { v[q] = row0[q * 16]; w[q] = row1[q * 16]; }
-          dft8(v);
-          dft8(w);
+          for (int bi = 0; bi < BT; bi++) {
+            const float2* row = tile + (rr + NG * (i0 + bi)) * TS + kb * 130 + j1;
+            #pragma unroll
+            for (int q = 0; q < 8; q++) v[bi][q] = row[q * 16];
+          }
           #pragma unroll
-          for (int q = 1; q < 8; q++) { v[q] = cmul(v[q], tw[q - 1]); w[q] = cmul(w[q], tw[q - 1]); }
+          for (int bi = 0; bi < BT; bi++) {
+            dft8(v[bi]);
+            #pragma unroll
+            for (int q = 1; q < 8; q++) v[bi][q] = cmul(v[bi][q], tw[q - 1]);
+          }
           #pragma unroll
-          for (int q = 0; q < 8; q++) { row0[q * 16] = v[q]; row1[q * 16] = w[q]; }
+          for (int bi = 0; bi < BT; bi++) {
+            float2* row = tile + (rr + NG * (i0 + bi)) * TS + kb * 130 + j1;
+            #pragma unroll
+            for (int q = 0; q < 8; q++) row[q * 16] = v[bi][q];
+          }
         }
       }
       bar_sync(BAR_FFT + rr, 128);
       #pragma unroll 1
-      for (int hh = 0; hh < 2; hh++) {               // pass 2: two radix-16 butterflies per thread
-        const int row_i = rr + 2 * ((tg >> 6) & 1) + 4 * hh, b = tg & 63;
+      for (int hh = 0; hh < RG / 2; hh++) {          // pass 2: one radix-16 butterfly per pair of rows of the group
+        const int row_i = rr + NG * ((tg >> 6) & 1) + 2 * NG * hh, b = tg & 63;
         const int kb = b & 7, kc = b >> 3;
         const float4* src = (const float4*)(tile + row_i * TS + kb * 130 + kc * 16);
         float2 v[16];
@@ -341,7 +367,7 @@ __global__ void __launch_bounds__(kNT, 1) k_chan_ring_ws(ChanParams prm, RingPar
           const float4 f4 = src[q];
           v[2 * q] = make_float2(f4.x, f4.y); v[2 * q + 1] = make_float2(f4.z, f4.w);
         }
-        if (hh == 1) bar_arrive(BAR_EMPTY + buf, kNT);   // this thread's last read of the tile is in registers
+        if (hh == RG / 2 - 1) bar_arrive(BAR_EMPTY + buf, NTH);   // this thread's last read of the tile is in registers
         dft16(v);
         const long long m = (a0 + row_i) * os + ph;
         if (m >= prm.row_base && m < prm.row_base + prm.nrows) {
