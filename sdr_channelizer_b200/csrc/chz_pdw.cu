@@ -160,52 +160,61 @@ __global__ void __launch_bounds__(256) k_select(uint32_t* __restrict__ hist, Sel
 }
 
 
-// grid: (channel groups of 4, row chunks).  block 256 = 64 rows x 4 channels per step (32-byte row
-// segments, i.e. whole DRAM sectors).
-// hist: [M][2][kBins] uint32.  Slot 0 is privatised in shared memory; slot 1 (only used when the two
-// order statistics have diverged into different buckets) goes straight to global atomics.
+// Local histogram of one radix pass of the per-channel median select.
+// grid: (slabs of 16 channels, row chunks); block 256 = 16 lanes across channels x 16 rows per step, so a warp's load is
+// two whole 128-byte lines (16 channels x 2 rows).  The first version gave a block FOUR channels (32-byte row segments,
+// 32-bit counters): eight sectors of eight different rows per warp load, 1.7 TB/s on a cold 45 MB matrix and
+// 2.3 TB/s on a 2 GB one; this one runs the 2 GB matrix at 5.8 TB/s (340 us per pass, 90 % of the copy peak).
+// Sixteen histograms of 2048 bins fit a block as 16-bit counters packed in pairs (64 KB, three blocks per SM); the host
+// keeps a block's row range below 65 536 so that no counter can overflow.  Channel c's counters start at word
+// c * 1025: the odd stride spreads equal bins of different channels (the rule: the channels' noise floors are alike)
+// over the banks.  M < 16 dividing 16: a "row" of 16 lanes is rpw = 16 / M consecutive matrix rows (all lanes busy,
+// loads still contiguous); other M < 16 or M % 16 != 0: the lanes past the last channel idle.
+// hist: [M][2][kBins] uint32.  Slot 0 is privatised in shared memory; slot 1 (only used when the two order statistics
+// have diverged into different buckets) goes straight to global atomics.
+// The select runs on |y|^2 (the operand of mag_of's square root): the correctly rounded square root is monotone, so
+// the k-th smallest |y| is the square root of the k-th smallest |y|^2 (thresholds_of takes it), and the binning loop
+// is a dozen instructions per element (with the square root, 64-bit row checks on every load and a branchy body it
+// was 76 and the pass was issue bound).  Whole batches of 8 loads skip the row checks; the last partial batch keeps them.
 // Tried and removed: running the select inside this launch, by the block that finishes a channel slab last (a ticket
-// per slab): the four selects of a slab then run one after the other in ONE block at the tail of the launch (about
+// per slab): the selects of a slab then run one after the other in ONE block at the tail of the launch (about
 // 5 us each: dependent global reads and four barriers) where k_select spreads them over M blocks -- 52 + 65 us for the
 // three passes against 34 + 46 us with the separate launches.
-__global__ void __launch_bounds__(256, 6) k_hist(const float2* __restrict__ y, long long nrows, int M, int pass,
-                                              const SelState* __restrict__ st, uint32_t* __restrict__ hist) {
-  __shared__ __align__(16) uint32_t sh[4 * kBins];
-  // on 100 ms files a block bins ~1 400 rows x 4 channels into 8 192 counters: clearing and flushing them costs as
-  // many shared-memory operations as the binning itself, so both go 16 bytes at a time
-  for (int i = threadIdx.x; i < kBins; i += 256) reinterpret_cast<uint4*>(sh)[i] = make_uint4(0u, 0u, 0u, 0u);
-  const int cl = threadIdx.x & 3, ch = blockIdx.x * 4 + cl;
-  const bool ch_ok = ch < M;                       // M need not be a multiple of 4
+constexpr int kH16Stride = kBins / 2 + 1;
+constexpr int kH16Smem = 16 * kH16Stride * (int)sizeof(uint32_t);
+__global__ void __launch_bounds__(256, 3) k_hist(const float2* __restrict__ y, long long nrows, int M, int pass, int rpw,
+                                                 const SelState* __restrict__ st, uint32_t* __restrict__ hist) {
+  extern __shared__ __align__(16) uint32_t sh16[];
+  for (int i = threadIdx.x; i < 16 * kH16Stride; i += 256) sh16[i] = 0;
+  const int lane16 = threadIdx.x & 15;
+  const int cl = rpw > 1 ? lane16 % M : lane16, sub = rpw > 1 ? lane16 / M : 0;
+  const int ch = blockIdx.x * 16 + cl;
+  const bool ch_ok = ch < M;
   const int shift = pass_shift(pass);
   const uint32_t bmask = pass_mask(pass), pmask = prefix_mask(pass);
   uint32_t p0 = 0, p1 = 0;
   if (pass > 0 && ch_ok) { p0 = st[ch].prefix[0]; p1 = st[ch].prefix[1]; }
   const bool split = p0 != p1;
   __syncthreads();
-  const long long rows_per_block = (nrows + gridDim.y - 1) / gridDim.y;
+  const long long rows_per_block = (nrows + gridDim.y - 1) / gridDim.y;   // <= 65 535 (host)
   const long long r_begin = (long long)blockIdx.y * rows_per_block;
   long long r_end = r_begin + rows_per_block;
   if (r_end > nrows) r_end = nrows;
-  // 8 independent loads in flight per thread: with one load per iteration the pass was latency bound
-  // (~2 TB/s); the loads are batched into registers first, then binned.
-  // The select runs on |y|^2 (the operand of mag_of's square root): the correctly rounded square root is monotone, so
-  // the k-th smallest |y| is the square root of the k-th smallest |y|^2 (thresholds_of takes it) -- and the binning
-  // loop is a dozen instructions per element instead of 55 (ncu: the pass was issue bound at 76 instructions per
-  // element, 25 us for 45 MB).  Whole batches skip the row checks; the last partial batch keeps them.
   constexpr int UN = 8;
-  uint32_t* const shc = sh + cl * kBins;
+  uint32_t* const shc = sh16 + cl * kH16Stride;
   uint32_t* const g1 = hist + ((size_t)ch * 2 + 1) * kBins;
   auto bin_one = [&](float2 v) {
     const uint32_t bits = __float_as_uint(mag2_of(v));
     const uint32_t pre = bits & pmask, bin = (bits >> shift) & bmask;
-    if (pre == p0) atomicAdd(shc + bin, 1u);
+    if (pre == p0) atomicAdd(shc + (bin >> 1), (bin & 1u) ? 0x10000u : 1u);
     if (split && pre == p1) atomicAdd(g1 + bin, 1u);
   };
   if (ch_ok) {
-    const long long rstep = 64LL * M;                       // elements between two loads of a thread
-    long long r = r_begin + (threadIdx.x >> 2);
+    const long long rs = 16LL * rpw;                        // rows per step of the block
+    const long long rstep = rs * M;                         // elements between two loads of a thread
+    long long r = r_begin + (long long)(threadIdx.x >> 4) * rpw + sub;
     const float2* p = y + r * M + ch;
-    for (; r + 64LL * (UN - 1) < r_end; r += 64 * UN, p += UN * rstep) {
+    for (; r + rs * (UN - 1) < r_end; r += rs * UN, p += UN * rstep) {
       float2 v[UN];
       #pragma unroll
       for (int u = 0; u < UN; u++) v[u] = __ldg(p + u * rstep);
@@ -215,22 +224,19 @@ __global__ void __launch_bounds__(256, 6) k_hist(const float2* __restrict__ y, l
     if (r < r_end) {                                       // last, partial batch: the same loads in flight, with row checks
       float2 v[UN];
       #pragma unroll
-      for (int u = 0; u < UN; u++) v[u] = r + 64LL * u < r_end ? __ldg(p + u * rstep) : make_float2(0.f, 0.f);
+      for (int u = 0; u < UN; u++) v[u] = r + rs * u < r_end ? __ldg(p + u * rstep) : make_float2(0.f, 0.f);
       #pragma unroll
-      for (int u = 0; u < UN; u++) if (r + 64LL * u < r_end) bin_one(v[u]);
+      for (int u = 0; u < UN; u++) if (r + rs * u < r_end) bin_one(v[u]);
     }
   }
   __syncthreads();
-  for (int i4 = threadIdx.x; i4 < kBins; i4 += 256) {
-    const uint4 q = reinterpret_cast<const uint4*>(sh)[i4];
-    if (!(q.x | q.y | q.z | q.w)) continue;
-    const int i = i4 * 4, c = blockIdx.x * 4 + i / kBins;      // kBins is a multiple of 4: the four counters share a channel
-    if (c >= M) continue;
-    uint32_t* g = &hist[((size_t)c * 2) * kBins + (i % kBins)];
-    if (q.x) atomicAdd(g, q.x);
-    if (q.y) atomicAdd(g + 1, q.y);
-    if (q.z) atomicAdd(g + 2, q.z);
-    if (q.w) atomicAdd(g + 3, q.w);
+  for (int i = threadIdx.x; i < 16 * (kBins / 2); i += 256) {
+    const int c = i / (kBins / 2), w = i % (kBins / 2);
+    const uint32_t v = sh16[c * kH16Stride + w];
+    if (!v || blockIdx.x * 16 + c >= M) continue;
+    uint32_t* g = hist + ((size_t)(blockIdx.x * 16 + c) * 2) * kBins + 2 * w;
+    if (v & 0xffffu) atomicAdd(g, v & 0xffffu);
+    if (v >> 16) atomicAdd(g + 1, v >> 16);
   }
 }
 
@@ -656,24 +662,31 @@ static int pdw_hist_pass(::chz* h, const float2* y, uint64_t nrows, int pass) {
   uint32_t* d_hist = (uint32_t*)h->pdw_hist.p;
   if (pass == 0) CHZ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)M * 2 * kBins * sizeof(uint32_t), st));
   if (nrows == 0) return CHZ_OK;
-  // exactly one wave: a second, partial wave doubles the pass time on 100 ms files.  How many blocks (32 KB of
-  // histogram each) fit an SM is asked, not assumed: the 1 KB the system reserves per block makes it 6, not 7,
-  // and sizing the grid for 7 ran every pass in 1.15 waves until ncu showed it (profiles/r02l_*).
-  static thread_local int occ_dev[kMaxDev] = {0};
+  // exactly one wave: a second, partial wave doubles the pass time on 100 ms files.  How many blocks fit an SM is
+  // asked, not assumed: the first version of the kernel (32 KB of histogram per block) was sized for 7 per SM where 6
+  // fit (the system reserves 1 KB per block) and ran every pass in 1.15 waves until ncu showed it (profiles/r02l_*).
+  static thread_local int occ_dev[kMaxDev] = {};
   int& occ = occ_dev[h->device % kMaxDev];
   if (!occ) {
     int nb = 0;
-    CHZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_hist, 256, 0));
+    CHZ_CUDA(cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, kH16Smem));
+    CHZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_hist, 256, kH16Smem));
     occ = nb > 0 ? nb : 1;
   }
-  long long ychunks = ((long long)h->sm_count * occ) / ((M + 3) / 4);
+  const int slabs = (M + 15) / 16;
+  const int rpw = (M < 16 && 16 % M == 0) ? 16 / M : 1;   // matrix rows per 16-lane row of the block
+  const long long wave = std::max<long long>(1, ((long long)h->sm_count * occ) / slabs);
+  long long ychunks = wave;
   static const int hc_env = std::getenv("CHZ_PDW_HIST_CHUNKS") ? std::atoi(std::getenv("CHZ_PDW_HIST_CHUNKS")) : 0;   // tuning aid
   if (hc_env > 0) ychunks = hc_env;
   const long long max_chunks = (long long)((nrows + 255) / 256);
   if (ychunks > max_chunks) ychunks = max_chunks;
   if (ychunks < 1) ychunks = 1;
+  const long long need = (long long)((nrows + 65534) / 65535);   // 16-bit counters: at most 65 535 rows per block, in whole waves
+  if (ychunks < need) ychunks = (need + wave - 1) / wave * wave;
   if (ychunks > 65535) ychunks = 65535;
-  k_hist<<<dim3((M + 3) / 4, (unsigned)ychunks), 256, 0, st>>>(y, (long long)nrows, M, pass, (const SelState*)h->pdw_sel.p, d_hist);
+  if ((long long)((nrows + ychunks - 1) / ychunks) > 65535) return CHZ_EINVAL;   // > 4.29e9 rows: not reachable (uint32 ranks)
+  k_hist<<<dim3(slabs, (unsigned)ychunks), 256, kH16Smem, st>>>(y, (long long)nrows, M, pass, rpw, (const SelState*)h->pdw_sel.p, d_hist);
   h->launches++;
   CHZ_CUDA(cudaGetLastError());
   return CHZ_OK;
