@@ -145,6 +145,22 @@ def test_cuda_graph_extractor_equals_direct_launches(monkeypatch):
     assert out["1"][0][0] == out["1"][1][0] == out["1"][3][0]
 
 
+@pytest.mark.parametrize("M,rows", [(56, 4001), (3, 9000), (2, 70001), (20, 1234), (16, 300), (4, 257), (48, 66000)])
+def test_noise_floor_is_the_exact_median_for_any_channel_count(M, rows):
+    """The histogram kernel gives a block 16 channels (lanes past the last channel idle; for M < 16 dividing 16 a
+    16-lane row is 16/M matrix rows) and packs its counters in 16 bits, with the host keeping a block below 65 536
+    rows.  The per-channel noise floor must be the median of the fp32 magnitudes for every such shape, with odd and
+    even row counts; channels get different scales so that their selects differ."""
+    rng = np.random.default_rng(M * 1000 + rows)
+    scale = (1.0 + np.arange(M)) / M
+    y = ((rng.standard_normal((rows, M)) + 1j * rng.standard_normal((rows, M))) * scale * 0.01).astype(np.complex64)
+    recs, nf = _pdws_on_matrix(y, 1e6 * M)
+    x, yy = y.real.astype(np.float64), y.imag.astype(np.float64)
+    mag = np.sqrt((x * x + np.float32(1) * (yy * yy)).astype(np.float32)).astype(np.float32)   # |y| in fp32
+    assert recs == []
+    assert np.allclose(nf, np.median(mag.astype(np.float64), axis=0), rtol=3e-7, atol=0)
+
+
 def test_no_pulses_and_empty():
     rng = np.random.default_rng(0)
     y = (rng.standard_normal((1000, 16)) + 1j * rng.standard_normal((1000, 16))).astype(np.complex64)
