@@ -47,3 +47,5 @@ def test_b200_arm_line():
     p = d["parity"]["configs[1]"]
     assert p["ok"] and p["rows_checked"] >= 32 and p["max_rel_rms"] <= 1e-5
     assert d["e2e_pdw"]["value"] > 0 and 0 < r["frac_sustained"] < 1.2
+    n = r["same_traffic_noop"]                           # K1 alone over the same buffers: what this traffic mix reaches
+    assert 0 < n["frac_of_peak"] < 1.2 and n["ms_per_launch"] > 0 and abs(n["this_kernel_vs_noop"] * r["ms_per_launch"] - n["ms_per_launch"]) < 1e-9
